@@ -1,0 +1,194 @@
+/*
+ * scht.h — C ABI of the B200-native Semi-convex Hull Tree k-NN query path.
+ *
+ * This is the drop-in boundary: exactly what a binding of the reference's GPU back-end
+ * (Code/GPU_Convex_Tree.h) would bind instead of OpenCL.  extern "C", plain pointers and sizes,
+ * no C++/torch types.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference repo, XiaoLHu/Semi-convex_Hull_Tree).
+ *
+ * Conventions
+ *   - every function returns SCHT_OK (0) or a negative scht_status; no exception crosses the ABI;
+ *     scht_last_error() returns a thread-local, human-readable message for the last failure.
+ *   - there is NO CPU fallback: every query entry point fails with SCHT_ERR_NO_DEVICE / SCHT_ERR_CUDA
+ *     when no sm_100 device (or no CUDA driver) is present.
+ *   - output buffers are caller-allocated; a handle is not thread-safe (like the reference).
+ *   - FLOAT_TYPE is float (Code/cyw_types.h:5-16, USE_DOUBLE 0); indices are int32 (the reference uses int).
+ */
+#ifndef SCHT_H_INCLUDED
+#define SCHT_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCHT_ABI_VERSION 1
+/* K limit of the device path. The reference's OpenCL path hard-codes MAX_NN_NUM=100
+ * (Code/GPU_Convex_Tree.h:466, kernels/do_kNN_gpu.cl:360-362) without checking; we check. */
+#define SCHT_MAX_K 128
+
+typedef enum scht_status {
+    SCHT_OK = 0,
+    SCHT_ERR_INVALID_ARG = -1,  /* NULL pointer, K<1, K>SCHT_MAX_K, negative sizes, bad percent ... */
+    SCHT_ERR_DIM_MISMATCH = -2, /* query dim != tree dim (Code/Convex_Tree.h:458-461 prints and returns) */
+    SCHT_ERR_NO_DEVICE = -3,    /* no CUDA device / not sm_100: the product has no CPU fallback */
+    SCHT_ERR_CUDA = -4,         /* a CUDA runtime call or kernel failed; see scht_last_error() */
+    SCHT_ERR_OOM = -5,          /* host or device allocation failed */
+    SCHT_ERR_DEGENERATE = -6,   /* tree build: unsplittable node (more than leaf-threshold identical rows) */
+    SCHT_ERR_INTERNAL = -7
+} scht_status;
+
+/* ------------------------------------------------------------------------------------------------
+ * Flat host-side description of a built tree — the SoA restatement of what
+ * GPU_Convex_Tree<T>::init_openCL_sorted_data_set flattens out of Convex_Tree<T>::nodes
+ * (Code/GPU_Convex_Tree.h:522-748) and of CONVEX_TREE (Code/ConvexNode.h:243-250).
+ *
+ * Node ids are the reference's creation order = DFS pre-order (Code/Convex_Tree.h:725,739);
+ * leaf ids are node-index order of leaves (Code/Convex_Tree.h:685-705); sorted_points holds the
+ * dataset re-ordered so that each leaf is contiguous (sort_raw_data, Code/Convex_Tree.h:593-633).
+ *
+ * Constraints: node i at depth k (root = depth 0) has k half-spaces  a_j . x + b_j >= 0.
+ * a_j is the unit normal of the j-th edge on the root->i path, stored ONCE per node as
+ * node_normal[path_node] (the last ALPHA row of that node, Code/Convex_Tree.h:767; the right
+ * child's is the exact negation of the left's, :848).  b_j is re-tightened per node
+ * (Code/Convex_Tree.h:760-766,771): node_beta[node_beta_off[i] + j], j = 0..k-1, root-side first.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct scht_tree_desc {
+    int32_t dim;      /* D */
+    int64_t n_points; /* N (< 2^31) */
+    int32_t n_nodes;
+    int32_t n_leaves;
+    int32_t depth;          /* reference's `depth` statistic (Code/Convex_Tree.h:285,837-839); informational */
+    int32_t leaf_threshold; /* (int)(N*pct), Code/Convex_Tree.h:525; informational */
+
+    const float* sorted_points;    /* [N*D]   m_sorted_data (Code/Convex_Tree.h:322) */
+    const int32_t* sorted_to_orig; /* [N]     m_sorted_data_ori_indexes (:323) */
+
+    const int32_t* leaf_start;   /* [L] leaf_nodes_start_pos_in_data_set (:325) */
+    const int32_t* leaf_count;   /* [L] ConvexNode::pts_number (Code/ConvexNode.h:45) */
+    const int32_t* leaf_node_id; /* [L] leaf_nodes_ori_indexes (Code/Convex_Tree.h:348) */
+
+    const int32_t* node_left;       /* [n_nodes] ConvexNode::left  (-1 for leaves) */
+    const int32_t* node_right;      /* [n_nodes] ConvexNode::right (-1 for leaves) */
+    const int32_t* node_parent;     /* [n_nodes] ConvexNode::parent_index (-1 for root) */
+    const int32_t* node_leaf_index; /* [n_nodes] leaf id, -1 for internal nodes */
+
+    const float* node_left_center;  /* [n_nodes*D] ConvexNode::left_center  (zeros for leaves) */
+    const float* node_right_center; /* [n_nodes*D] ConvexNode::right_center (zeros for leaves) */
+    const float* node_normal;       /* [n_nodes*D] last ALPHA row of the node (zeros for root) */
+    const int32_t* node_beta_off;   /* [n_nodes+1] CSR offsets into node_beta; off[i+1]-off[i] = depth(i) */
+    const float* node_beta;         /* [sum depth] ConvexNode::BETA */
+} scht_tree_desc;
+
+/* ------------------------------------------------------------------------------------------------
+ * Host tree builder.  Restates Convex_Tree<T>'s constructor path
+ * (Code/Convex_Tree.h:518-548 -> build_tree :708-857 -> build_simplified_tree :685-705 ->
+ * sort_raw_data :593-633) with the reference's float/double arithmetic and its libc rand() stream
+ * (glibc TYPE_3 generator re-implemented, seeded like srand(seed); seed 1 == "srand never called"),
+ * so the flat arrays are bit-identical to the reference's tree for the same input and seed.
+ * Pure host code; needs no GPU.
+ *
+ * leaf_pts_percent must be in (0, 0.5) — the reference throws std::runtime_error otherwise
+ * (Code/Convex_Tree.h:522-523); here: SCHT_ERR_INVALID_ARG.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct scht_host_tree scht_host_tree;
+
+int scht_build_tree(const float* data, int64_t n_points, int32_t dim, float leaf_pts_percent,
+                    uint32_t rand_seed, scht_host_tree** out);
+/* Borrowed view; valid until scht_host_tree_free. */
+const scht_tree_desc* scht_host_tree_desc(const scht_host_tree* tree);
+/* Seconds spent in build_tree+build_simplified_tree (timer_build_tree, Code/Convex_Tree.h:532-539). */
+double scht_host_tree_build_seconds(const scht_host_tree* tree);
+void scht_host_tree_free(scht_host_tree* tree);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device tree + query.  Replaces GPU_Convex_Tree<T>'s constructor tail
+ * (init_openCL_device / init_openCL_sorted_data_set, Code/GPU_Convex_Tree.h:150-163,431-479,522-748)
+ * and its do_kNN / do_brute_force_kNN (Code/GPU_Convex_Tree.h:208-323,328-427) together with the
+ * two OpenCL kernels (Code/kernels/do_kNN_gpu.cl:298-446,462-536).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct scht_handle scht_handle;
+
+/* Counters of one query call; mirror the reference's statistics surface
+ * (Code/GPU_Convex_Tree.h:57-65,950-971; Code/Convex_Tree.h:288-296). */
+typedef struct scht_stats {
+    int64_t n_queries;
+    int64_t dist_computations;   /* (query,point) distances the exact leaf scan evaluated, incl. the approximate leaf */
+    int64_t dist_useful;         /* the subset belonging to (query,leaf) pairs that were not pruned for that query */
+    int64_t hyperplane_tests;    /* (query,node) lower-bound tests ("quadprog calls") */
+    int64_t descent_dists;       /* 2 per level of the approximate-leaf descent (dist_computation_times_in_host) */
+    int64_t batches;             /* "batch iteration times" (Code/GPU_Convex_Tree.h:968) */
+    double ms_total;             /* wall time of the call (timer_whole_alg) */
+    double ms_device;            /* CUDA-event time of the device work of the call */
+    double ms_scan;              /* CUDA-event time of the leaf-scan kernel(s) only */
+    int64_t scan_launches;       /* number of leaf-scan kernel launches */
+    int64_t kernel_launches;     /* number of kernels launched by the call */
+} scht_stats;
+
+/* Uploads the tree to `device` (CUDA ordinal) in the device layout described in DESIGN.md. */
+int scht_create(const scht_tree_desc* tree, int device, scht_handle** out);
+void scht_destroy(scht_handle* h);
+
+/* BATCH_SIZE_OF_QUERY_POINTS_PUSCH_TO_DEVICE (Code/Convex_Tree.h:352, set_batch_size
+ * Code/GPU_Convex_Tree.h:197-204): queries are streamed through the device in batches of this
+ * many.  Default 1,000,000 (Code/main.cc:670).  batch_size < 1 -> SCHT_ERR_INVALID_ARG. */
+int scht_set_batch_size(scht_handle* h, int64_t batch_size);
+
+/* Exact k-NN of n_queries host-resident queries ([n_queries*dim] row-major).  Host->device copy of
+ * the queries and device->host copy of the results are part of the call (== kNN() + get_kNN_*,
+ * Code/Convex_Tree.h:456-469,231-238).
+ *   idx_out   [n_queries*K] original point indices (get_kNN_indexes), -1 where fewer than K points exist
+ *   dist2_out [n_queries*K] ascending squared distances (get_kNN_dists_squre), FLT_MAX for empty slots
+ *   dist_out  [n_queries*K] optional (may be NULL): sqrtf(dist2) (get_kNN_dists)
+ * Result contract: bit-identical to CPU_Convex_Tree (Code/CPU_Convex_Tree.h:380-430): the K smallest
+ * (dist2, approx-leaf-first, sorted position) triples; see DESIGN.md "Result contract". */
+int scht_query(scht_handle* h, const float* queries, int64_t n_queries, int32_t dim, int32_t K,
+               int32_t* idx_out, float* dist2_out, float* dist_out, scht_stats* stats /* may be NULL */);
+
+/* Same computation with queries and outputs already resident in device memory of the handle's GPU
+ * (device pointers; row-major as above).  Runs on `cuda_stream` (a cudaStream_t cast to void*; NULL =
+ * the handle's own stream) and returns after enqueueing + synchronising that stream. */
+int scht_query_device(scht_handle* h, const float* d_queries, int64_t n_queries, int32_t dim, int32_t K,
+                      int32_t* d_idx_out, float* d_dist2_out, float* d_dist_out, void* cuda_stream,
+                      scht_stats* stats);
+
+/* Exhaustive search over all points, same result contract with "approximate leaf" = none, i.e. ties
+ * go to the lower ORIGINAL index (brute_force_kNN / do_brute_force_kNN,
+ * Code/Convex_Tree.h:473-486, Code/GPU_Convex_Tree.h:328-427, kernels/do_kNN_gpu.cl:462-536). */
+int scht_brute_force(scht_handle* h, const float* queries, int64_t n_queries, int32_t dim, int32_t K,
+                     int32_t* idx_out, float* dist2_out, float* dist_out, scht_stats* stats);
+
+/* Approximate-leaf descent only (do_find_approximate_nodes, Code/GPU_Convex_Tree.h:168-193):
+ * leaf_out[i] = leaf index reached by query i. Host buffers. */
+int scht_find_approximate_leaves(scht_handle* h, const float* queries, int64_t n_queries, int32_t dim,
+                                 int32_t* leaf_out);
+
+/* ---- sharded-dataset mode: one GPU scans only leaves [leaf_begin, leaf_end) ---------
+ * scht_query_partial_device writes, per query, K sorted 64-bit keys
+ *     key = (float_bits(dist2) << 32) | (is_not_approx_leaf << 31) | sorted_position
+ * (FLT_MAX-keyed for empty slots) into d_keys_out [n_queries*K]; lists from different leaf ranges are
+ * merged exactly by scht_merge_partial_device (n_lists lists laid out [n_lists][n_queries][K]), which
+ * also maps positions back to original indices and writes the final idx/dist2/dist arrays.
+ * The exchange between the two calls (NCCL all-to-all over NVLink) is done by the caller. */
+int scht_query_partial_device(scht_handle* h, const float* d_queries, int64_t n_queries, int32_t dim, int32_t K,
+                              int32_t leaf_begin, int32_t leaf_end, uint64_t* d_keys_out, void* cuda_stream,
+                              scht_stats* stats);
+int scht_merge_partial_device(scht_handle* h, const uint64_t* d_keys, int32_t n_lists, const float* d_queries,
+                              int64_t n_queries, int32_t dim, int32_t K, int32_t* d_idx_out, float* d_dist2_out,
+                              float* d_dist_out, void* cuda_stream);
+
+/* Tree facts of a handle (for logs: print_tree_info, Code/Convex_Tree.h:946-958). */
+int scht_handle_info(const scht_handle* h, int32_t* dim, int64_t* n_points, int32_t* n_nodes, int32_t* n_leaves,
+                     int32_t* device, int64_t* device_bytes);
+
+const char* scht_last_error(void);
+int scht_abi_version(void);
+/* Number of visible CUDA devices (0 if none / no driver); never fails. */
+int scht_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCHT_H_INCLUDED */
