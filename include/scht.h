@@ -115,8 +115,9 @@ typedef struct scht_handle scht_handle;
  * (Code/GPU_Convex_Tree.h:57-65,950-971; Code/Convex_Tree.h:288-296). */
 typedef struct scht_stats {
     int64_t n_queries;
-    int64_t dist_computations;   /* (query,point) distances the exact leaf scan evaluated, incl. the approximate leaf */
-    int64_t dist_useful;         /* the subset belonging to (query,leaf) pairs that were not pruned for that query */
+    int64_t dist_computations;   /* (query,point) distances the leaf scan evaluated, incl. the approximate leaves (S_gpu) */
+    int64_t exact_reevaluations; /* pairs re-evaluated with the reference's float/double arithmetic (near the K-th distance) */
+    int64_t list_insertions;     /* successful top-K insertions (NNResult::update hits, Code/Convex_Tree.h:121-151) */
     int64_t hyperplane_tests;    /* (query,node) lower-bound tests ("quadprog calls") */
     int64_t descent_dists;       /* 2 per level of the approximate-leaf descent (dist_computation_times_in_host) */
     int64_t batches;             /* "batch iteration times" (Code/GPU_Convex_Tree.h:968) */

@@ -1,0 +1,602 @@
+// CUDA side of the C ABI (include/scht.h): device tree upload and the batched exact k-NN query.
+//
+// Replaces GPU_Convex_Tree<T>'s OpenCL host code (reference: Code/GPU_Convex_Tree.h:150-163 ctor tail,
+// :522-748 init_openCL_sorted_data_set, :208-323 do_kNN, :328-427 do_brute_force_kNN).  One handle = one GPU,
+// one stream.  There is no CPU fallback: without an sm_100 device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/scht.h"
+#include "scht_error.h"
+#include "scht_kernels.cuh"
+
+using namespace scht;
+
+#define CU_TRY(expr)                                                                                              \
+    do {                                                                                                          \
+        cudaError_t e__ = (expr);                                                                                 \
+        if (e__ != cudaSuccess)                                                                                   \
+            return scht::fail(e__ == cudaErrorMemoryAllocation ? SCHT_ERR_OOM : SCHT_ERR_CUDA,                   \
+                              std::string(#expr) + ": " + cudaGetErrorString(e__));                             \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct scht_handle {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    DevTree T{};
+    int depth = 0;
+    std::vector<void*> owned;  // device allocations of the tree
+    size_t tree_bytes = 0;
+    int64_t batch_size = 1000000;  // Code/main.cc:670
+    int scan_variant = 1;
+    std::vector<int> h_leaf_start, h_leaf_count;
+    DevBuf q, q_leaf, hist, q_order, state, ranges, n_ranges, idx, d2, dist, counters, leaf_tmp;
+};
+
+namespace {
+
+template <class T>
+int upload(scht_handle* h, const T* src, size_t count, const T** dst) {
+    void* d = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CU_TRY(cudaMalloc(&d, bytes));
+    h->owned.push_back(d);
+    h->tree_bytes += bytes;
+    if (count) CU_TRY(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    *dst = reinterpret_cast<const T*>(d);
+    return SCHT_OK;
+}
+
+// Leaf-scan kernel variants: consumer warps per CTA x resident CTAs per SM the register budget is sized for.
+//   0: 8 warps (64 queries/tile), 1 CTA/SM   1: 7 warps (56 queries/tile, 256 threads with the producer), 2 CTAs/SM
+//   2: 4 warps (32 queries/tile), 3 CTAs/SM
+constexpr int kVariantWarps[3] = {8, 7, 4};
+int pick_variant(const scht_handle* h, int K) {
+    int v = h->scan_variant;
+    int nw = kVariantWarps[v];
+    if ((int)scan_smem_bytes(nw, h->T.dpad, K) <= h->max_smem) return v;
+    if ((int)scan_smem_bytes(4, h->T.dpad, K) <= h->max_smem) return 2;
+    return -1;
+}
+
+template <int NW, int MINB>
+int launch_scan_t(scht_handle* h, const ScanParams& P, cudaStream_t s) {
+    size_t smem = scan_smem_bytes(NW, P.T.dpad, P.K);
+    CU_TRY(cudaFuncSetAttribute(k_scan<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int tq = NW * kQPerWarp;
+    int n_tiles = (P.nq + tq - 1) / tq;
+    k_scan<NW, MINB><<<n_tiles, (NW + 1) * 32, smem, s>>>(P);
+    CU_TRY(cudaGetLastError());
+    return SCHT_OK;
+}
+int launch_scan(scht_handle* h, int variant, const ScanParams& P, cudaStream_t s) {
+    switch (variant) {
+        case 0: return launch_scan_t<8, 1>(h, P, s);
+        case 1: return launch_scan_t<7, 2>(h, P, s);
+        default: return launch_scan_t<4, 3>(h, P, s);
+    }
+}
+
+int launch_traverse(scht_handle* h, const TraverseParams& P, cudaStream_t s) {
+    int tq = P.tq;
+    int n_tiles = (P.nq + tq - 1) / tq;
+    int warps = 4;
+    const int slots = (tq > 32) ? 64 : 32;
+    while (warps > 1 && (int)traverse_smem_bytes(warps, slots, P.T.dpad) > h->max_smem) warps >>= 1;
+    size_t smem = traverse_smem_bytes(warps, slots, P.T.dpad);
+    if ((int)smem > h->max_smem) return scht::fail(SCHT_ERR_INVALID_ARG, "dimension too large for the traversal kernel");
+    int blocks = (n_tiles + warps - 1) / warps;
+    if (tq > 32) {
+        CU_TRY(cudaFuncSetAttribute(k_traverse<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_traverse<2><<<blocks, warps * 32, smem, s>>>(P);
+    } else {
+        CU_TRY(cudaFuncSetAttribute(k_traverse<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_traverse<1><<<blocks, warps * 32, smem, s>>>(P);
+    }
+    CU_TRY(cudaGetLastError());
+    return SCHT_OK;
+}
+
+struct QueryOut {
+    int32_t* idx = nullptr;   // device
+    float* d2 = nullptr;      // device
+    float* dist = nullptr;    // device, optional
+    uint64_t* keys = nullptr; // device, partial mode
+};
+
+// One batch, everything on the device.  brute: exhaustive scan keyed by original index.  partial: only leaves
+// [leaf_lo,leaf_hi) and keys out.
+int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool partial, int leaf_lo, int leaf_hi, const QueryOut& out,
+              cudaStream_t s, scht_stats* st, bool timed) {
+    const int variant = pick_variant(h, K);
+    if (variant < 0) return scht::fail(SCHT_ERR_INVALID_ARG, "dimension * K too large for the leaf-scan kernel's shared memory");
+    const int tq = kVariantWarps[variant] * kQPerWarp;
+    const int n_tiles = (nq + tq - 1) / tq;
+    const DevTree& T = h->T;
+
+    CU_TRY(h->q_leaf.reserve((size_t)nq * 4));
+    CU_TRY(h->q_order.reserve((size_t)nq * 4));
+    CU_TRY(h->hist.reserve((size_t)(T.n_leaves + 1) * 4));
+    CU_TRY(h->counters.reserve(8 * 8));
+    CU_TRY(cudaMemsetAsync(h->counters.p, 0, 64, s));
+    unsigned long long* ctr = h->counters.as<unsigned long long>();
+
+    ScanParams P{};
+    P.T = T;
+    P.q = d_q;
+    P.q_order = h->q_order.as<int>();
+    P.q_leaf = h->q_leaf.as<int>();
+    P.nq = nq;
+    P.K = K;
+    P.pos_lo = 0;
+    P.pos_hi = T.n_points;
+    P.idx_out = out.idx;
+    P.d2_out = out.d2;
+    P.dist_out = out.dist;
+    P.keys_out = out.keys;
+    P.counters = ctr;
+    int launches = 0, scans = 0;
+
+    if (timed) CU_TRY(cudaEventRecord(h->ev[0], s));
+    if (brute) {
+        k_iota<<<(nq + 255) / 256, 256, 0, s>>>(h->q_order.as<int>(), nq);
+        launches++;
+        P.mode = kScanAll;
+        P.write_mode = kWriteFinal;
+        if (timed) CU_TRY(cudaEventRecord(h->ev[1], s));
+        int rc = launch_scan(h, variant, P, s);
+        if (rc) return rc;
+        launches++;
+        scans++;
+        if (timed) {
+            CU_TRY(cudaEventRecord(h->ev[2], s));
+            CU_TRY(cudaEventRecord(h->ev[3], s));
+            CU_TRY(cudaEventRecord(h->ev[4], s));
+        }
+    } else {
+        // K1 descend + leaf histogram, K3 bucketing
+        CU_TRY(cudaMemsetAsync(h->hist.p, 0, (size_t)(T.n_leaves + 1) * 4, s));
+        k_descend<<<(nq + 127) / 128, 128, 0, s>>>(T, d_q, nq, h->q_leaf.as<int>(), h->hist.as<int>(), ctr);
+        k_scan_hist<<<1, 1024, 0, s>>>(h->hist.as<int>(), T.n_leaves);
+        k_scatter<<<(nq + 255) / 256, 256, 0, s>>>(h->q_leaf.as<int>(), nq, h->hist.as<int>(), h->q_order.as<int>());
+        CU_TRY(cudaGetLastError());
+        launches += 3;
+        if (timed) CU_TRY(cudaEventRecord(h->ev[1], s));
+
+        CU_TRY(h->state.reserve((size_t)nq * K * 8));
+        CU_TRY(h->ranges.reserve((size_t)n_tiles * kRangeCap * sizeof(int2)));
+        CU_TRY(h->n_ranges.reserve((size_t)n_tiles * 4));
+        P.state = h->state.as<uint64_t>();
+        P.ranges = h->ranges.as<int2>();
+        P.n_ranges = h->n_ranges.as<int>();
+        if (partial) {
+            // positions of the shard: leaves [leaf_lo, leaf_hi) are contiguous in the sorted matrix
+            P.pos_lo = (leaf_lo < T.n_leaves) ? h->h_leaf_start[leaf_lo] : T.n_points;
+            P.pos_hi = (leaf_hi > leaf_lo) ? h->h_leaf_start[leaf_hi - 1] + h->h_leaf_count[leaf_hi - 1] : P.pos_lo;
+        }
+        // K4a seed scan of the approximate leaves
+        P.mode = kScanSeed;
+        P.write_mode = kWriteState;
+        int rc = launch_scan(h, variant, P, s);
+        if (rc) return rc;
+        launches++;
+        scans++;
+        if (timed) CU_TRY(cudaEventRecord(h->ev[2], s));
+        // K2 traversal with the seed bounds -> page ranges per tile
+        TraverseParams TP{};
+        TP.T = T;
+        TP.q = d_q;
+        TP.q_order = P.q_order;
+        TP.q_leaf = P.q_leaf;
+        TP.nq = nq;
+        TP.K = K;
+        TP.tq = tq;
+        TP.state = P.state;
+        TP.ranges = h->ranges.as<int2>();
+        TP.n_ranges = h->n_ranges.as<int>();
+        TP.leaf_lo = leaf_lo;
+        TP.leaf_hi = leaf_hi;
+        TP.counters = ctr;
+        rc = launch_traverse(h, TP, s);
+        if (rc) return rc;
+        launches++;
+        if (timed) CU_TRY(cudaEventRecord(h->ev[3], s));
+        // K4b main scan
+        P.mode = kScanList;
+        P.write_mode = partial ? kWriteKeys : kWriteFinal;
+        rc = launch_scan(h, variant, P, s);
+        if (rc) return rc;
+        launches++;
+        scans++;
+        if (timed) CU_TRY(cudaEventRecord(h->ev[4], s));
+    }
+    if (st) {
+        unsigned long long c[8];
+        CU_TRY(cudaMemcpyAsync(c, ctr, 64, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        st->n_queries += nq;
+        st->dist_computations += (int64_t)c[0];
+        st->exact_reevaluations += (int64_t)c[1];
+        st->list_insertions += (int64_t)c[2];
+        st->hyperplane_tests += (int64_t)c[4];
+        st->descent_dists += (int64_t)c[3];
+        st->batches += 1;
+        st->scan_launches += scans;
+        st->kernel_launches += launches;
+        if (timed) {
+            float a = 0, b = 0, c2 = 0;
+            CU_TRY(cudaEventElapsedTime(&a, h->ev[0], h->ev[4]));
+            CU_TRY(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+            CU_TRY(cudaEventElapsedTime(&c2, h->ev[3], h->ev[4]));
+            st->ms_device += a;
+            st->ms_scan += b + c2;
+        }
+    }
+    return SCHT_OK;
+}
+
+int check_query_args(const scht_handle* h, const void* q, int64_t nq, int32_t dim, int32_t K, const void* idx, const void* d2) {
+    if (!h) return scht::fail(SCHT_ERR_INVALID_ARG, "handle is NULL");
+    if (nq < 0 || nq > 0x7fffffffLL) return scht::fail(SCHT_ERR_INVALID_ARG, "n_queries out of range");
+    if (K < 1 || K > SCHT_MAX_K) return scht::fail(SCHT_ERR_INVALID_ARG, "K must be in [1, SCHT_MAX_K]");
+    if (dim != h->T.dim) {
+        // Code/Convex_Tree.h:458-461 prints "dimension of query points is not the same as the data" and returns
+        return scht::fail(SCHT_ERR_DIM_MISMATCH, "query dimension " + std::to_string(dim) + " != tree dimension " + std::to_string(h->T.dim));
+    }
+    if (nq > 0 && (!q || !idx || !d2)) return scht::fail(SCHT_ERR_INVALID_ARG, "NULL query or output buffer");
+    return SCHT_OK;
+}
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int host_query(scht_handle* h, const float* queries, int64_t n_queries, int32_t dim, int32_t K, int32_t* idx_out, float* dist2_out,
+               float* dist_out, scht_stats* stats, bool brute) {
+    int rc = check_query_args(h, queries, n_queries, dim, K, idx_out, dist2_out);
+    if (rc) return rc;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    double t0 = now_ms();
+    CU_TRY(cudaSetDevice(h->device));
+    int64_t bs = std::min<int64_t>(h->batch_size, 0x7fffffffLL / std::max(K, dim));
+    for (int64_t b0 = 0; b0 < n_queries; b0 += bs) {
+        int nq = (int)std::min<int64_t>(bs, n_queries - b0);
+        CU_TRY(h->q.reserve((size_t)nq * dim * 4));
+        CU_TRY(h->idx.reserve((size_t)nq * K * 4));
+        CU_TRY(h->d2.reserve((size_t)nq * K * 4));
+        if (dist_out) CU_TRY(h->dist.reserve((size_t)nq * K * 4));
+        CU_TRY(cudaMemcpyAsync(h->q.p, queries + (size_t)b0 * dim, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, h->stream));
+        QueryOut out;
+        out.idx = h->idx.as<int32_t>();
+        out.d2 = h->d2.as<float>();
+        out.dist = dist_out ? h->dist.as<float>() : nullptr;
+        rc = run_batch(h, h->q.as<float>(), nq, K, brute, false, 0, h->T.n_leaves, out, h->stream, stats, stats != nullptr);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(idx_out + (size_t)b0 * K, out.idx, (size_t)nq * K * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaMemcpyAsync(dist2_out + (size_t)b0 * K, out.d2, (size_t)nq * K * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (dist_out) CU_TRY(cudaMemcpyAsync(dist_out + (size_t)b0 * K, out.dist, (size_t)nq * K * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (stats) stats->ms_total = now_ms() - t0;
+    return SCHT_OK;
+}
+
+}  // namespace
+
+extern "C" int scht_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** out) {
+    if (!out) return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: out is NULL");
+    *out = nullptr;
+    if (!t || t->dim < 1 || t->n_points < 1 || t->n_points > 0x7fffff00LL || t->n_nodes < 1 || t->n_leaves < 1 || !t->sorted_points ||
+        !t->sorted_to_orig || !t->leaf_start || !t->leaf_count || !t->leaf_node_id || !t->node_left || !t->node_right || !t->node_parent ||
+        !t->node_leaf_index || !t->node_left_center || !t->node_right_center || !t->node_normal || !t->node_beta_off || !t->node_beta)
+        return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: incomplete tree description");
+    int ndev = scht_device_count();
+    if (ndev == 0) return scht::fail(SCHT_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: bad device ordinal");
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return scht::fail(SCHT_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this library is built for sm_100a only");
+
+    const int nn = t->n_nodes, L = t->n_leaves, dim = t->dim;
+    const int64_t N = t->n_points;
+    // ---- validate the structure and derive per-node records (host) -------------------------------------------
+    std::vector<NodeRec> rec((size_t)nn);
+    for (int i = 0; i < nn; i++) {
+        bool leaf = t->node_leaf_index[i] >= 0;
+        if (leaf != (t->node_left[i] < 0) || leaf != (t->node_right[i] < 0)) return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: node child links inconsistent");
+        if (!leaf && (t->node_left[i] != i + 1 || t->node_right[i] <= i + 1 || t->node_right[i] >= nn))
+            return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: nodes must be numbered in DFS pre-order (left child = id+1)");
+        if (leaf && t->node_leaf_index[i] >= L) return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: leaf index out of range");
+        rec[i].depth = t->node_beta_off[i + 1] - t->node_beta_off[i];
+        rec[i].beta_off = t->node_beta_off[i];
+        rec[i].leaf = leaf ? t->node_leaf_index[i] : -1;
+        rec[i].right = leaf ? -1 : t->node_right[i];
+        rec[i].pad = 0;
+    }
+    int depth = 0;
+    for (int i = nn - 1; i >= 0; i--) {
+        if (rec[i].leaf >= 0) {
+            int li = rec[i].leaf;
+            rec[i].size = 1;
+            rec[i].pos0 = t->leaf_start[li];
+            rec[i].pos1 = t->leaf_start[li] + t->leaf_count[li];
+            if (rec[i].pos0 < 0 || rec[i].pos1 > N || t->leaf_count[li] < 0) return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: leaf range out of bounds");
+        } else {
+            int l = i + 1, r = rec[i].right;
+            rec[i].size = 1 + rec[l].size + rec[r].size;
+            if (l + rec[l].size != r) return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: nodes are not in DFS pre-order");
+            if (rec[l].pos1 != rec[r].pos0) return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: leaves are not contiguous in DFS order");
+            rec[i].pos0 = rec[l].pos0;
+            rec[i].pos1 = rec[r].pos1;
+            if (rec[l].depth != rec[i].depth + 1 || rec[r].depth != rec[i].depth + 1)
+                return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: node_beta_off does not match node depth");
+        }
+        depth = std::max(depth, rec[i].depth);
+    }
+    if (rec[0].size != nn || rec[0].pos0 != 0 || rec[0].pos1 != N || rec[0].depth != 0)
+        return scht::fail(SCHT_ERR_INVALID_ARG, "scht_create: tree does not cover the data set");
+
+    scht_handle* h = new scht_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    h->depth = depth;
+    h->h_leaf_start.assign(t->leaf_start, t->leaf_start + L);
+    h->h_leaf_count.assign(t->leaf_count, t->leaf_count + L);
+    if (const char* ev = getenv("SCHT_SCAN_VARIANT")) h->scan_variant = std::max(0, std::min(2, atoi(ev)));
+    auto fail_free = [&](int rc) {
+        scht_destroy(h);
+        return rc;
+    };
+#define TRY_H(x)                   \
+    do {                           \
+        int rc__ = (x);            \
+        if (rc__) return fail_free(rc__); \
+    } while (0)
+#define CU_H(expr)                                                                                           \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return fail_free(scht::fail(e__ == cudaErrorMemoryAllocation ? SCHT_ERR_OOM : SCHT_ERR_CUDA,    \
+                                        std::string(#expr) + ": " + cudaGetErrorString(e__)));              \
+    } while (0)
+    CU_H(cudaSetDevice(device));
+    CU_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) CU_H(cudaEventCreate(&e));
+
+    DevTree& T = h->T;
+    T.dim = dim;
+    T.dpad = (dim + 3) & ~3;
+    T.n_points = (int)N;
+    T.n_pages = (int)((N + kPage - 1) / kPage);
+    T.n_nodes = nn;
+    T.n_leaves = L;
+    const int dpad = T.dpad;
+
+    // padded copies of the per-node vectors
+    std::vector<float> nrm((size_t)nn * dpad, 0.f), lc((size_t)nn * dpad, 0.f), rc((size_t)nn * dpad, 0.f);
+    for (int i = 0; i < nn; i++) {
+        memcpy(&nrm[(size_t)i * dpad], t->node_normal + (size_t)i * dim, sizeof(float) * dim);
+        memcpy(&lc[(size_t)i * dpad], t->node_left_center + (size_t)i * dim, sizeof(float) * dim);
+        memcpy(&rc[(size_t)i * dpad], t->node_right_center + (size_t)i * dim, sizeof(float) * dim);
+    }
+    TRY_H(upload(h, rec.data(), rec.size(), &T.nodes));
+    TRY_H(upload(h, t->node_beta, (size_t)t->node_beta_off[nn], &T.node_beta));
+    TRY_H(upload(h, nrm.data(), nrm.size(), &T.node_normal));
+    TRY_H(upload(h, lc.data(), lc.size(), &T.node_lc));
+    TRY_H(upload(h, rc.data(), rc.size(), &T.node_rc));
+    TRY_H(upload(h, t->leaf_start, (size_t)L, &T.leaf_start));
+    TRY_H(upload(h, t->leaf_count, (size_t)L, &T.leaf_count));
+    {
+        std::vector<int32_t> oi((size_t)T.n_pages * kPage, -1);
+        memcpy(oi.data(), t->sorted_to_orig, sizeof(int32_t) * (size_t)N);
+        TRY_H(upload(h, oi.data(), oi.size(), &T.orig_idx));
+        CU_H(cudaStreamSynchronize(h->stream));
+    }
+    // max ||x||_2 (double, rounded up) for the pruning margin
+    {
+        double mx = 0;
+        for (int64_t i = 0; i < N; i++) {
+            double s = 0;
+            const float* p = t->sorted_points + (size_t)i * dim;
+            for (int j = 0; j < dim; j++) s += (double)p[j] * p[j];
+            mx = std::max(mx, s);
+        }
+        T.xnorm_max = (float)(std::sqrt(mx) * 1.0001);
+        if (!(T.xnorm_max < 3.0e38f)) T.xnorm_max = 3.0e38f;
+    }
+    // pages: upload row-major slabs and transpose on the device
+    {
+        float* pages = nullptr;
+        size_t pbytes = (size_t)T.n_pages * dpad * kPage * 4;
+        CU_H(cudaMalloc(&pages, pbytes));
+        h->owned.push_back(pages);
+        h->tree_bytes += pbytes;
+        T.pages = pages;
+        const int64_t slab = 4 << 20;  // rows per slab
+        DevBuf tmp;
+        CU_H(tmp.reserve((size_t)std::min<int64_t>(slab, (int64_t)T.n_pages * kPage) * dim * 4));
+        const int64_t total_rows = (int64_t)T.n_pages * kPage;
+        for (int64_t r0 = 0; r0 < total_rows; r0 += slab) {
+            int64_t nr = std::min<int64_t>(slab, total_rows - r0);
+            int64_t real = std::max<int64_t>(0, std::min<int64_t>(nr, N - r0));
+            if (real > 0) CU_H(cudaMemcpyAsync(tmp.p, t->sorted_points + (size_t)r0 * dim, (size_t)real * dim * 4, cudaMemcpyHostToDevice, h->stream));
+            int64_t work = nr * dpad;
+            k_build_pages<<<(unsigned)((work + 255) / 256), 256, 0, h->stream>>>(tmp.as<float>(), r0, nr, dim, dpad, N, pages);
+            CU_H(cudaGetLastError());
+            CU_H(cudaStreamSynchronize(h->stream));
+        }
+        tmp.release();
+    }
+    CU_H(cudaStreamSynchronize(h->stream));
+#undef TRY_H
+#undef CU_H
+    *out = h;
+    return SCHT_OK;
+}
+
+extern "C" void scht_destroy(scht_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->owned) cudaFree(p);
+    for (DevBuf* b : {&h->q, &h->q_leaf, &h->hist, &h->q_order, &h->state, &h->ranges, &h->n_ranges, &h->idx, &h->d2, &h->dist, &h->counters, &h->leaf_tmp})
+        b->release();
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int scht_set_batch_size(scht_handle* h, int64_t batch_size) {
+    if (!h || batch_size < 1) return scht::fail(SCHT_ERR_INVALID_ARG, "scht_set_batch_size: batch_size must be >= 1");
+    h->batch_size = batch_size;
+    return SCHT_OK;
+}
+
+extern "C" int scht_query(scht_handle* h, const float* queries, int64_t n_queries, int32_t dim, int32_t K, int32_t* idx_out,
+                          float* dist2_out, float* dist_out, scht_stats* stats) {
+    return host_query(h, queries, n_queries, dim, K, idx_out, dist2_out, dist_out, stats, false);
+}
+
+extern "C" int scht_brute_force(scht_handle* h, const float* queries, int64_t n_queries, int32_t dim, int32_t K, int32_t* idx_out,
+                                float* dist2_out, float* dist_out, scht_stats* stats) {
+    return host_query(h, queries, n_queries, dim, K, idx_out, dist2_out, dist_out, stats, true);
+}
+
+extern "C" int scht_query_device(scht_handle* h, const float* d_queries, int64_t n_queries, int32_t dim, int32_t K, int32_t* d_idx_out,
+                                 float* d_dist2_out, float* d_dist_out, void* cuda_stream, scht_stats* stats) {
+    int rc = check_query_args(h, d_queries, n_queries, dim, K, d_idx_out, d_dist2_out);
+    if (rc) return rc;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    double t0 = now_ms();
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    int64_t bs = std::min<int64_t>(h->batch_size, 0x7fffffffLL / std::max(K, dim));
+    for (int64_t b0 = 0; b0 < n_queries; b0 += bs) {
+        int nq = (int)std::min<int64_t>(bs, n_queries - b0);
+        QueryOut out;
+        out.idx = d_idx_out + (size_t)b0 * K;
+        out.d2 = d_dist2_out + (size_t)b0 * K;
+        out.dist = d_dist_out ? d_dist_out + (size_t)b0 * K : nullptr;
+        rc = run_batch(h, d_queries + (size_t)b0 * dim, nq, K, false, false, 0, h->T.n_leaves, out, s, stats, stats != nullptr);
+        if (rc) return rc;
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    if (stats) stats->ms_total = now_ms() - t0;
+    return SCHT_OK;
+}
+
+extern "C" int scht_find_approximate_leaves(scht_handle* h, const float* queries, int64_t n_queries, int32_t dim, int32_t* leaf_out) {
+    if (!h) return scht::fail(SCHT_ERR_INVALID_ARG, "handle is NULL");
+    if (dim != h->T.dim) return scht::fail(SCHT_ERR_DIM_MISMATCH, "query dimension != tree dimension");
+    if (n_queries < 0 || n_queries > 0x7fffffffLL / std::max(1, dim) || (n_queries > 0 && (!queries || !leaf_out)))
+        return scht::fail(SCHT_ERR_INVALID_ARG, "scht_find_approximate_leaves: bad arguments");
+    if (n_queries == 0) return SCHT_OK;
+    CU_TRY(cudaSetDevice(h->device));
+    int nq = (int)n_queries;
+    CU_TRY(h->q.reserve((size_t)nq * dim * 4));
+    CU_TRY(h->q_leaf.reserve((size_t)nq * 4));
+    CU_TRY(cudaMemcpyAsync(h->q.p, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, h->stream));
+    k_descend<<<(nq + 127) / 128, 128, 0, h->stream>>>(h->T, h->q.as<float>(), nq, h->q_leaf.as<int>(), nullptr, nullptr);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(leaf_out, h->q_leaf.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return SCHT_OK;
+}
+
+extern "C" int scht_query_partial_device(scht_handle* h, const float* d_queries, int64_t n_queries, int32_t dim, int32_t K,
+                                         int32_t leaf_begin, int32_t leaf_end, uint64_t* d_keys_out, void* cuda_stream, scht_stats* stats) {
+    int rc = check_query_args(h, d_queries, n_queries, dim, K, d_keys_out, d_keys_out);
+    if (rc) return rc;
+    if (leaf_begin < 0 || leaf_end > h->T.n_leaves || leaf_begin > leaf_end) return scht::fail(SCHT_ERR_INVALID_ARG, "bad leaf range");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_queries == 0) return SCHT_OK;
+    double t0 = now_ms();
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    int64_t bs = std::min<int64_t>(h->batch_size, 0x7fffffffLL / std::max(K, dim));
+    for (int64_t b0 = 0; b0 < n_queries; b0 += bs) {
+        int nq = (int)std::min<int64_t>(bs, n_queries - b0);
+        QueryOut out;
+        out.keys = d_keys_out + (size_t)b0 * K;
+        rc = run_batch(h, d_queries + (size_t)b0 * dim, nq, K, false, true, leaf_begin, leaf_end, out, s, stats, stats != nullptr);
+        if (rc) return rc;
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    if (stats) stats->ms_total = now_ms() - t0;
+    return SCHT_OK;
+}
+
+extern "C" int scht_merge_partial_device(scht_handle* h, const uint64_t* d_keys, int32_t n_lists, const float* d_queries, int64_t n_queries,
+                                         int32_t dim, int32_t K, int32_t* d_idx_out, float* d_dist2_out, float* d_dist_out, void* cuda_stream) {
+    (void)d_queries;
+    int rc = check_query_args(h, d_keys, n_queries, dim, K, d_idx_out, d_dist2_out);
+    if (rc) return rc;
+    if (n_lists < 1 || n_lists > 16) return scht::fail(SCHT_ERR_INVALID_ARG, "n_lists must be in [1,16]");
+    if (n_queries == 0) return SCHT_OK;
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    int nq = (int)n_queries;
+    k_merge_partial<<<(nq + 127) / 128, 128, 0, s>>>(h->T, d_keys, n_lists, nq, K, d_idx_out, d_dist2_out, d_dist_out);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s));
+    return SCHT_OK;
+}
+
+extern "C" int scht_handle_info(const scht_handle* h, int32_t* dim, int64_t* n_points, int32_t* n_nodes, int32_t* n_leaves, int32_t* device,
+                                int64_t* device_bytes) {
+    if (!h) return scht::fail(SCHT_ERR_INVALID_ARG, "handle is NULL");
+    if (dim) *dim = h->T.dim;
+    if (n_points) *n_points = h->T.n_points;
+    if (n_nodes) *n_nodes = h->T.n_nodes;
+    if (n_leaves) *n_leaves = h->T.n_leaves;
+    if (device) *device = h->device;
+    if (device_bytes) *device_bytes = (int64_t)h->tree_bytes;
+    return SCHT_OK;
+}

@@ -1,0 +1,767 @@
+// sm_100a device code of the Semi-convex Hull Tree exact k-NN query path.
+//
+// Replaces the reference's OpenCL kernels (Code/kernels/do_kNN_gpu.cl:298-446 do_finding_KNN_by_leaf_order,
+// :462-536 do_brute_force_KNN) and the host descent loop (Code/GPU_Convex_Tree.h:168-193).  Not a port: the
+// reference is thread-per-query with private arrays; here queries are bucketed by approximate leaf into tiles of
+// 8 queries per warp, a producer lane streams "pages" (256 sorted points, dim-major) into shared memory with
+// cp.async.bulk + mbarriers, and every staged page is reused by all queries of the tile.
+//
+// RESULT CONTRACT: for every query the K smallest keys
+//     key = float_bits(d2) << 32 | r << 31 | pos
+// d2  = the reference's distance arithmetic acc = (float)((double)acc + (double)d*(double)d), d = fl32(p_j - q_j),
+//       j ascending (Code/basic_functions.h:167-198),
+// r   = 0 for points of the query's approximate leaf, else 1 (the reference scans that leaf first,
+//       Code/CPU_Convex_Tree.h:181-217, and NNResult::update keeps the first arrival among equals,
+//       Code/Convex_Tree.h:121-151),
+// pos = row in the leaf-sorted point matrix (leaves are visited in ascending order, Code/CPU_Convex_Tree.h:386-427).
+// The hot loop evaluates d2 with packed FP32 FMAs (FADD2/FFMA2, one rounding per step); any pair that comes within
+// 2^-20 (relative) of the query's current K-th distance is re-evaluated with the reference's float/double
+// arithmetic before it is compared, so accepted values are the reference's bit for bit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace scht {
+
+constexpr int kPage = 256;         // sorted points per page
+constexpr int kRowsPerStage = 16;  // dims per shared-memory stage (16 rows x 256 floats = 16 KB)
+constexpr int kStages = 4;
+constexpr int kQPerWarp = 8;       // queries owned by one consumer warp
+constexpr int kMaxLevel = 64;      // constraints beyond this depth are ignored by the pruning bound (still valid)
+constexpr int kRangeCap = 128;     // page ranges per tile; overflow coalesces gaps (scans more, stays exact)
+constexpr uint64_t kEmptyKey = 0x7f7fffffffffffffull;  // FLT_MAX bits (INFINITE, Code/cyw_types.h:18) | all ones
+constexpr float kPadCoord = 3.0e38f;                    // coordinate of padded positions: d2 overflows to +inf
+
+struct __align__(32) NodeRec {
+    int size;      // nodes in the subtree (DFS pre-order: subtree = [id, id+size))
+    int depth;     // root = 0; the node has `depth` constraints
+    int beta_off;  // into node_beta
+    int pos0, pos1;  // sorted-position range covered by the subtree
+    int leaf;      // leaf index, -1 for internal nodes
+    int right;     // right child id (left child = id+1), -1 for leaves
+    int pad;
+};
+
+struct DevTree {
+    int dim, dpad, n_points, n_pages, n_nodes, n_leaves;
+    const float* pages;       // [n_pages][dpad][256]
+    const int* orig_idx;      // [n_pages*256], -1 on padded positions
+    const NodeRec* nodes;     // [n_nodes]
+    const float* node_beta;   // CSR by NodeRec::beta_off, root-side constraint first
+    const float* node_normal; // [n_nodes][dpad] the node's own (last) constraint normal, zero padded
+    const float* node_lc;     // [n_nodes][dpad] left centre
+    const float* node_rc;     // [n_nodes][dpad] right centre
+    const int* leaf_start;    // [n_leaves]
+    const int* leaf_count;    // [n_leaves]
+    float xnorm_max;          // max ||x||_2 over the data set (pruning margin)
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion counted on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// packed FP32 pairs (Blackwell FADD2 / FFMA2): two IEEE fp32 lanes per instruction, each rounded like the scalar op
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// The reference's accumulation step: result(float) += pow(d, 2) evaluated in double (Code/basic_functions.h:177,194).
+__device__ __forceinline__ float ref_acc_sq(float acc, float d) { return (float)((double)acc + (double)d * (double)d); }
+
+// ---------------------------------------------------------------------------------------------------------
+// page builder: row-major sorted points -> dim-major pages
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_build_pages(const float* __restrict__ rows, int64_t row0, int64_t nrows, int dim, int dpad, int64_t n_points,
+                              float* __restrict__ pages) {
+    // one thread per (position, dim) of the pages touched by rows [row0, row0+nrows) rounded to pages
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = nrows * dpad;
+    if (i >= total) return;
+    int64_t r = i / dpad;
+    int j = (int)(i - r * dpad);
+    int64_t pos = row0 + r;
+    float v = (j < dim) ? ((pos < n_points) ? rows[r * dim + j] : kPadCoord) : 0.f;
+    int64_t page = pos / kPage;
+    int lane = (int)(pos - page * kPage);
+    pages[(page * dpad + j) * kPage + lane] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: approximate-leaf descent (replaces the host loop Code/GPU_Convex_Tree.h:168-193 == Code/CPU_Convex_Tree.h:181-197)
+// thread per query; the two centre distances use the reference arithmetic so the branch decisions are identical.
+// Also histograms the leaves (first step of the bucketing).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_descend(DevTree T, const float* __restrict__ q, int nq, int* __restrict__ q_leaf, int* __restrict__ leaf_hist,
+                          unsigned long long* __restrict__ counters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const float* qi = q + (size_t)i * T.dim;
+    int node = 0, levels = 0;
+    NodeRec nr = T.nodes[0];
+    while (nr.leaf < 0) {
+        const float* lc = T.node_lc + (size_t)node * T.dpad;
+        const float* rc = T.node_rc + (size_t)node * T.dpad;
+        float l = 0.f, r = 0.f;
+        for (int j = 0; j < T.dim; j++) {
+            float x = qi[j];
+            l = ref_acc_sq(l, x - lc[j]);
+            r = ref_acc_sq(r, x - rc[j]);
+        }
+        node = (l >= r) ? nr.right : node + 1;  // ties go right (Code/CPU_Convex_Tree.h:191)
+        nr = T.nodes[node];
+        levels++;
+    }
+    q_leaf[i] = nr.leaf;
+    if (leaf_hist) atomicAdd(&leaf_hist[nr.leaf], 1);
+    if (counters) atomicAdd(&counters[3], (unsigned long long)(2 * levels));
+}
+
+// K3a: exclusive scan of the leaf histogram (single CTA; n_leaves is at most a few hundred thousand)
+__global__ void k_scan_hist(int* __restrict__ hist, int n) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int v = (i < n) ? hist[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int s = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_sums[lane] = s;  // inclusive
+        }
+        __syncthreads();
+        int carry = carry_s;
+        int excl = carry + (w > 0 ? warp_sums[w - 1] : 0) + x - v;
+        if (i < n) hist[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_sums[(blockDim.x >> 5) - 1];
+        __syncthreads();
+    }
+}
+
+// K3b: scatter query ids into their leaf bucket -> q_order (queries sharing an approximate leaf become neighbours,
+// so one tile's queries want the same pages).  Order inside a bucket is arbitrary; results do not depend on it.
+__global__ void k_scatter(const int* __restrict__ q_leaf, int nq, int* __restrict__ cursor, int* __restrict__ q_order) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int slot = atomicAdd(&cursor[q_leaf[i]], 1);
+    q_order[slot] = i;
+}
+__global__ void k_iota(int* __restrict__ a, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4: leaf scan + top-K
+// ---------------------------------------------------------------------------------------------------------
+enum ScanMode : int {
+    kScanAll = 0,   // every page, keys carry the ORIGINAL index, no approximate-leaf priority (brute force entry)
+    kScanSeed = 1,  // pages covering the approximate leaves of the tile's queries; lists start empty
+    kScanList = 2,  // page ranges produced by the traversal kernel; lists resume from `state`
+};
+
+enum WriteMode : int { kWriteFinal = 1, kWriteState = 0, kWriteKeys = 2 };
+
+struct ScanParams {
+    DevTree T;
+    const float* q;        // [nq][dim] row-major, caller order
+    const int* q_order;    // [nq] sorted slot -> query id
+    const int* q_leaf;     // [nq] approximate leaf by query id (unused in kScanAll)
+    int nq, K;
+    int mode;
+    int write_mode;        // kWriteFinal / kWriteState / kWriteKeys
+    int pos_lo, pos_hi;    // only positions in [pos_lo,pos_hi) may enter the lists (sharded-dataset mode)
+    const int2* ranges;    // [n_tiles][kRangeCap] page ranges [x,y) (kScanList)
+    const int* n_ranges;   // [n_tiles]
+    uint64_t* state;       // [nq][K] keys by sorted slot
+    uint64_t* keys_out;    // [nq][K] keys by query id (kWriteKeys)
+    int* idx_out;          // [nq][K]
+    float* d2_out;         // [nq][K]
+    float* dist_out;       // [nq][K] or NULL
+    unsigned long long* counters;  // [0] scanned (query,point) pairs, [1] exact re-evaluations, [2] list insertions
+};
+
+__host__ __device__ inline size_t scan_smem_bytes(int n_cwarps, int dpad, int K) {
+    size_t tq = (size_t)n_cwarps * kQPerWarp;
+    size_t b = (size_t)kStages * kRowsPerStage * kPage * 4;  // stages
+    b += (size_t)dpad * tq * 4;                              // queries, dim-major
+    b += tq * (size_t)K * 8;                                 // lists
+    b += tq * 8 + tq * 3 * 4 + 16;                           // seed ranges, a0, a1, qid, misc
+    b += 2 * kStages * 8 + 64;                               // barriers
+    return b;
+}
+
+// Warp-cooperative sorted insert of `key` into L[0..K) (ascending, unique keys); the last element drops out.
+// Idempotent: a key already present is ignored, so re-scanning a page can never duplicate a neighbour.
+__device__ __forceinline__ int list_insert(uint64_t* L, int K, uint64_t key, int lane) {
+    uint64_t nv[4];
+    bool dup = false;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        int i = s * 32 + lane;
+        nv[s] = 0;
+        if (i < K) {
+            uint64_t cur = L[i];
+            uint64_t prev = (i > 0) ? L[i - 1] : 0ull;
+            dup |= (cur == key);
+            nv[s] = (cur < key) ? cur : ((i == 0 || prev < key) ? key : prev);
+        }
+    }
+    if (__any_sync(0xffffffffu, dup)) return 0;
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        int i = s * 32 + lane;
+        if (i < K) L[i] = nv[s];
+    }
+    __syncwarp();
+    return 1;
+}
+
+// Ascending, merged page ranges covering the approximate leaves of a tile's (leaf-sorted) queries.
+__device__ inline int build_seed_ranges(const int* a0s, const int* a1s, int nq_tile, int pos_lo, int pos_hi, int2* out) {
+    int n = 0;
+    for (int i = 0; i < nq_tile; i++) {
+        int a0 = max(a0s[i], pos_lo), a1 = min(a1s[i], pos_hi);
+        if (a1 <= a0) continue;
+        int pb = a0 / kPage, pe = (a1 + kPage - 1) / kPage;
+        if (n > 0 && pb <= out[n - 1].y) {
+            out[n - 1].y = max(out[n - 1].y, pe);
+            if (pb < out[n - 1].x) out[n - 1].x = pb;  // cannot happen for leaf-sorted queries; keeps the list valid
+        } else {
+            out[n++] = make_int2(pb, pe);
+        }
+    }
+    return n;
+}
+
+// Walks the pages of a tile: the ranges of `list`, minus (optionally) the pages of `seed`.  Producer and consumers
+// run the same walk, so they agree on the stage sequence without communicating.
+struct PageWalk {
+    const int2* list;
+    int n_list;
+    const int2* seed;
+    int n_seed;  // 0: nothing to skip
+    int r, page, sr;
+    __device__ PageWalk(const int2* l, int nl, const int2* s, int ns) : list(l), n_list(nl), seed(s), n_seed(ns), r(0), sr(0) {
+        page = (nl > 0) ? l[0].x : 0;
+    }
+    __device__ bool next(int& out) {
+        for (;;) {
+            while (r < n_list && page >= list[r].y) {
+                r++;
+                if (r < n_list) page = max(page, list[r].x);
+            }
+            if (r >= n_list) return false;
+            while (sr < n_seed && seed[sr].y <= page) sr++;
+            if (sr < n_seed && page >= seed[sr].x) {
+                page = seed[sr].y;
+                continue;
+            }
+            out = page++;
+            return true;
+        }
+    }
+};
+
+template <int NW, int MINB>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P) {
+    constexpr int TQ = NW * kQPerWarp;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const DevTree& T = P.T;
+    const int dpad = T.dpad, K = P.K;
+    float* stage_mem = reinterpret_cast<float*>(smem_raw);
+    float* qs = stage_mem + kStages * kRowsPerStage * kPage;  // [dpad][TQ]
+    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)dpad * TQ);
+    int2* seed_rg = reinterpret_cast<int2*>(lists + (size_t)TQ * K);  // [TQ]
+    int* a0s = reinterpret_cast<int*>(seed_rg + TQ);
+    int* a1s = a0s + TQ;
+    int* qids = a1s + TQ;
+    int* misc = qids + TQ;  // [0] number of seed ranges
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc + 4);
+    uint64_t* empty_bar = full_bar + kStages;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int q_begin = tile * TQ;
+    const int nq_tile = min(TQ, P.nq - q_begin);
+
+    // ---- tile set-up -------------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < TQ; i += blockDim.x) {
+        int qid = (i < nq_tile) ? P.q_order[q_begin + i] : -1;
+        qids[i] = qid;
+        int a0 = 0, a1 = 0;
+        if (qid >= 0 && P.mode != kScanAll) {
+            int leaf = P.q_leaf[qid];
+            a0 = T.leaf_start[leaf];
+            a1 = a0 + T.leaf_count[leaf];
+        }
+        a0s[i] = a0;
+        a1s[i] = a1;
+    }
+    __syncthreads();
+    for (int i = tid; i < TQ * dpad; i += blockDim.x) {
+        int qi = i / dpad, j = i - qi * dpad;
+        int qid = qids[qi];
+        float v = (qid >= 0 && j < T.dim) ? P.q[(size_t)qid * T.dim + j] : 0.f;
+        qs[j * TQ + qi] = v;
+    }
+    if (P.mode == kScanList) {
+        for (int i = tid; i < TQ * K; i += blockDim.x) {
+            int qi = i / K;
+            lists[i] = (qi < nq_tile) ? P.state[(size_t)(q_begin + qi) * K + (i - qi * K)] : kEmptyKey;
+        }
+    } else {
+        for (int i = tid; i < TQ * K; i += blockDim.x) lists[i] = kEmptyKey;
+    }
+    if (tid == 0) misc[0] = (P.mode == kScanAll) ? 0 : build_seed_ranges(a0s, a1s, nq_tile, P.pos_lo, P.pos_hi, seed_rg);
+    __syncthreads();
+
+    // ---- the page list of this tile (identical walk in the producer and in every consumer warp) ------------
+    const int n_seed = misc[0];
+    const int2 all_pages = make_int2(0, T.n_pages);
+    const int2* list;
+    int n_list, n_skip = 0;
+    if (P.mode == kScanAll) {
+        list = &all_pages;
+        n_list = 1;
+    } else if (P.mode == kScanSeed) {
+        list = seed_rg;
+        n_list = n_seed;
+    } else {
+        list = P.ranges + (size_t)tile * kRangeCap;
+        n_list = P.n_ranges[tile];
+        n_skip = n_seed;  // pages of the seed scan are already in the lists
+    }
+    PageWalk walk(list, n_list, seed_rg, n_skip);
+    const int n_slices = (dpad + kRowsPerStage - 1) / kRowsPerStage;
+    int page;
+
+    if (warp == NW) {
+        // ================= producer: one lane streams page slices through the stage ring =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            while (walk.next(page)) {
+                for (int s = 0; s < n_slices; s++, it++) {
+                    int st = it % kStages;
+                    uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(&empty_bar[st], ph ^ 1);
+                    int rows = min(kRowsPerStage, dpad - s * kRowsPerStage);
+                    uint32_t bytes = (uint32_t)rows * kPage * 4;
+                    mbar_arrive_expect_tx(&full_bar[st], bytes);
+                    bulk_g2s(stage_mem + (size_t)st * kRowsPerStage * kPage,
+                             T.pages + ((size_t)page * dpad + (size_t)s * kRowsPerStage) * kPage, bytes, &full_bar[st]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ================= consumers: warp owns 8 queries, lane owns 8 points of every page =====================
+    const int qw0 = warp * kQPerWarp;  // first tile-local query of this warp
+    uint64_t* my_lists = lists + (size_t)qw0 * K;
+    // fast-path bound per query: K-th d2 widened by 2^-20 (covers the rare double-rounding difference between the
+    // packed FMA chain and the reference arithmetic); padded query slots get -1 and never collect.
+    float thr[kQPerWarp];
+#pragma unroll
+    for (int qi = 0; qi < kQPerWarp; qi++) {
+        float kth = __uint_as_float((uint32_t)(my_lists[(size_t)qi * K + K - 1] >> 32));
+        thr[qi] = (qw0 + qi < nq_tile) ? fminf(kth * 1.000001f, 3.402823466e+38f) : -1.f;
+    }
+    const bool brute = (P.mode == kScanAll);
+    unsigned long long n_pairs = 0;
+    unsigned int n_exact = 0, n_ins = 0;
+
+    uint32_t it = 0;
+    while (walk.next(page)) {
+        uint64_t acc[kQPerWarp][4];
+#pragma unroll
+        for (int qi = 0; qi < kQPerWarp; qi++)
+#pragma unroll
+            for (int pp = 0; pp < 4; pp++) acc[qi][pp] = 0ull;
+
+        for (int s = 0; s < n_slices; s++, it++) {
+            int st = it % kStages;
+            uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&full_bar[st], ph);
+            const float* sp = stage_mem + (size_t)st * kRowsPerStage * kPage + 4 * lane;
+            const float* qp = qs + (size_t)s * kRowsPerStage * TQ + qw0;
+            int rows = min(kRowsPerStage, dpad - s * kRowsPerStage);
+#pragma unroll 1
+            for (int row = 0; row < rows; row += 4) {
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++) {
+                    float4 pa = *reinterpret_cast<const float4*>(sp + (row + rr) * kPage);
+                    float4 pb = *reinterpret_cast<const float4*>(sp + (row + rr) * kPage + 128);
+                    float4 qa = *reinterpret_cast<const float4*>(qp + (row + rr) * TQ);
+                    float4 qb = *reinterpret_cast<const float4*>(qp + (row + rr) * TQ + 4);
+                    uint64_t pv[4] = {pack2(pa.x, pa.y), pack2(pa.z, pa.w), pack2(pb.x, pb.y), pack2(pb.z, pb.w)};
+                    float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                    for (int qi = 0; qi < kQPerWarp; qi++) {
+                        uint64_t qq = pack2(qv[qi], qv[qi]);  // becomes the scalar-broadcast operand form of FADD2
+#pragma unroll
+                        for (int pp = 0; pp < 4; pp++) {
+                            uint64_t d = sub2(pv[pp], qq);
+                            acc[qi][pp] = fma2(d, d, acc[qi][pp]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+        }
+        n_pairs += (unsigned long long)min(kPage, T.n_points - page * kPage);
+
+        // ---- candidate filter: anything within the widened K-th distance goes to the exact path ----------
+        bool any = false;
+#pragma unroll
+        for (int qi = 0; qi < kQPerWarp; qi++)
+#pragma unroll
+            for (int pp = 0; pp < 4; pp++) {
+                float lo, hi;
+                unpack2(acc[qi][pp], lo, hi);
+                any |= (lo <= thr[qi]) | (hi <= thr[qi]);
+            }
+        if (__any_sync(0xffffffffu, any)) {
+            // per-lane candidate mask: bit 8*qi+e  <->  query qi, point e of this lane
+            // (e = 2*pp+h: positions 4*lane+{0..3} for e<4, 128+4*lane+{0..3} for e>=4)
+            uint32_t cm_lo = 0, cm_hi = 0;
+#pragma unroll
+            for (int qi = 0; qi < kQPerWarp; qi++)
+#pragma unroll
+                for (int pp = 0; pp < 4; pp++) {
+                    float lo, hi;
+                    unpack2(acc[qi][pp], lo, hi);
+                    uint32_t b = (lo <= thr[qi] ? 1u : 0u) | (hi <= thr[qi] ? 2u : 0u);
+                    if (qi < 4) cm_lo |= b << (8 * qi + 2 * pp);
+                    else cm_hi |= b << (8 * (qi - 4) + 2 * pp);
+                }
+            float new_thr[kQPerWarp];
+#pragma unroll 1
+            for (int qi = 0; qi < kQPerWarp; qi++) {
+                uint32_t bits = ((qi < 4 ? cm_lo : cm_hi) >> (8 * (qi & 3))) & 0xffu;
+                uint64_t* L = my_lists + (size_t)qi * K;
+                if (__any_sync(0xffffffffu, bits != 0)) {
+                    const int a0 = a0s[qw0 + qi], a1 = a1s[qw0 + qi];
+                    do {
+                        // every lane re-evaluates one of its own candidates with the reference arithmetic
+                        bool cand = false;
+                        float d2 = 0.f;
+                        int pos = 0;
+                        if (bits) {
+                            int e = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            int in_page = ((e >> 2) ? 128 : 0) + 4 * lane + (e & 3);
+                            pos = page * kPage + in_page;
+                            const float* pg = T.pages + (size_t)page * dpad * kPage + in_page;
+                            const float* qq = qs + qw0 + qi;
+                            for (int j = 0; j < T.dim; j++) d2 = ref_acc_sq(d2, pg[(size_t)j * kPage] - qq[j * TQ]);
+                            n_exact++;
+                            cand = (d2 < 3.402823466e+38f) && (pos >= P.pos_lo) && (pos < P.pos_hi);
+                        }
+                        unsigned m = __ballot_sync(0xffffffffu, cand);
+                        while (m) {
+                            int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            float cd2 = __shfl_sync(0xffffffffu, d2, src);
+                            int cpos = __shfl_sync(0xffffffffu, pos, src);
+                            uint32_t low = brute ? (uint32_t)T.orig_idx[cpos]
+                                                 : (((cpos >= a0 && cpos < a1) ? 0u : 0x80000000u) | (uint32_t)cpos);
+                            uint64_t key = ((uint64_t)__float_as_uint(cd2) << 32) | low;
+                            if (key < L[K - 1]) n_ins += list_insert(L, K, key, lane);
+                        }
+                    } while (__any_sync(0xffffffffu, bits != 0));
+                }
+                float kth = __uint_as_float((uint32_t)(L[K - 1] >> 32));
+                new_thr[qi] = (qw0 + qi < nq_tile) ? fminf(kth * 1.000001f, 3.402823466e+38f) : -1.f;
+            }
+#pragma unroll
+            for (int qi = 0; qi < kQPerWarp; qi++) thr[qi] = new_thr[qi];
+        }
+    }
+
+    // ---- results ------------------------------------------------------------------------------------------
+    __syncwarp();
+    for (int qi = 0; qi < kQPerWarp; qi++) {
+        if (qw0 + qi >= nq_tile) break;
+        const uint64_t* L = my_lists + (size_t)qi * K;
+        const int qid = qids[qw0 + qi];
+        if (P.write_mode == kWriteFinal) {
+            for (int k = lane; k < K; k += 32) {
+                uint64_t key = L[k];
+                int idx = -1;
+                float d2 = 3.402823466e+38f;
+                if (key != kEmptyKey) {
+                    uint32_t low = (uint32_t)key;
+                    idx = brute ? (int)low : T.orig_idx[low & 0x7fffffffu];
+                    d2 = __uint_as_float((uint32_t)(key >> 32));
+                }
+                P.idx_out[(size_t)qid * K + k] = idx;
+                P.d2_out[(size_t)qid * K + k] = d2;
+                if (P.dist_out) P.dist_out[(size_t)qid * K + k] = __fsqrt_rn(d2);
+            }
+        } else if (P.write_mode == kWriteState) {
+            for (int k = lane; k < K; k += 32) P.state[(size_t)(q_begin + qw0 + qi) * K + k] = L[k];
+        } else {
+            for (int k = lane; k < K; k += 32) P.keys_out[(size_t)qid * K + k] = L[k];
+        }
+    }
+    if (P.counters) {
+        int nvalid = max(0, min(kQPerWarp, nq_tile - qw0));
+        for (int o = 16; o; o >>= 1) n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+        if (lane == 0) {
+            atomicAdd(&P.counters[0], n_pairs * (unsigned long long)nvalid);
+            atomicAdd(&P.counters[1], (unsigned long long)n_exact);
+            atomicAdd(&P.counters[2], (unsigned long long)n_ins);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: traversal / pruning.  One warp per tile of TQ queries (lane = 2 queries for TQ=64), walking the tree in DFS
+// pre-order (= array order).  The dot product of a query with the normal of each edge on the current root->node
+// path is memoised per level in shared memory (the reference's `_pro` memo, Code/ConvexNode.h:151-206, but per
+// path level instead of per node id), so a node costs one D-dim dot + depth adds per query.  A subtree is
+// skipped when the lower bound of EVERY query of the tile exceeds that query's K-th distance after the seed scan
+// (bound: Code/ConvexNode.h:113-144, max over active constraints of -(a.q+b); it holds for every descendant
+// because a node's half-spaces contain all its points, Code/Convex_Tree.h:755-771).  Unlike the reference the
+// test carries a rounding margin, so the search stays provably exact.  Output: ascending page ranges per tile.
+// ---------------------------------------------------------------------------------------------------------
+struct TraverseParams {
+    DevTree T;
+    const float* q;
+    const int* q_order;
+    const int* q_leaf;
+    int nq, K, tq;           // tq = queries per tile of the leaf-scan kernel (<= 32*QL)
+    const uint64_t* state;   // [nq][K] keys after the seed scan
+    int2* ranges;            // [n_tiles][kRangeCap]
+    int* n_ranges;           // [n_tiles]
+    int leaf_lo, leaf_hi;    // only leaves in [leaf_lo, leaf_hi) are emitted (sharded-dataset mode)
+    unsigned long long* counters;  // [4] node tests (per query), [5] pages listed
+};
+
+__host__ __device__ inline size_t traverse_smem_bytes(int warps, int tq, int dpad) {
+    return (size_t)warps * ((size_t)dpad * tq * 4 + (size_t)kMaxLevel * tq * 4);
+}
+
+template <int QL>  // queries per lane: tile = 32*QL queries
+__global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
+    constexpr int TQ = 32 * QL;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const DevTree& T = P.T;
+    const int dpad = T.dpad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int tile = blockIdx.x * nwarps + warp;
+    const int n_tiles = (P.nq + P.tq - 1) / P.tq;
+    if (tile >= n_tiles) return;
+    float* qs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((size_t)dpad * TQ + (size_t)kMaxLevel * TQ);  // [dpad][TQ]
+    float* dots = qs + (size_t)dpad * TQ;                                                                            // [level][TQ]
+    const int q_begin = tile * P.tq;  // tile stride = the leaf-scan kernel's tile (<= TQ slots used)
+    const int nq_tile = min(P.tq, P.nq - q_begin);
+
+    float thr2[QL], absm[QL];
+    bool valid[QL];
+#pragma unroll
+    for (int u = 0; u < QL; u++) {
+        int qi = lane + 32 * u;
+        thr2[u] = 0.f;
+        absm[u] = 0.f;
+        valid[u] = false;  // padded slot: never keeps a subtree alive
+        if (qi < nq_tile) {
+            valid[u] = true;
+            int qid = P.q_order[q_begin + qi];
+            float n2 = 0.f;
+            for (int j = 0; j < dpad; j++) {
+                float v = (j < T.dim) ? P.q[(size_t)qid * T.dim + j] : 0.f;
+                qs[j * TQ + qi] = v;
+                n2 = fmaf(v, v, n2);
+            }
+            // rounding margin of the bound: |error| <= c * D * 2^-24 * (||q|| + max||x||), see DESIGN.md
+            absm[u] = 16.f * (float)(T.dim + 2) * 5.9604645e-8f * (sqrtf(n2) * 1.0001f + T.xnorm_max);
+            uint32_t kb = (uint32_t)(P.state[(size_t)(q_begin + qi) * P.K + P.K - 1] >> 32);
+            thr2[u] = __uint_as_float(kb) * 1.00001f;  // K-th d2 after the seed (FLT_MAX -> inf: never prunes)
+        } else {
+            for (int j = 0; j < dpad; j++) qs[j * TQ + qi] = 0.f;
+        }
+    }
+    __syncwarp();
+
+    int2* out = P.ranges + (size_t)tile * kRangeCap;
+    int n_out = 0, cur_b = -1, cur_e = -1;  // open range [cur_b, cur_e)
+    unsigned long long tests = 0, listed = 0;
+    // Append [b,e) (ascending).  When the tile runs out of slots the last range is widened over the gap: the extra
+    // pages only cost time (every scanned pair is evaluated exactly and list insertion is idempotent).
+    auto flush = [&](int b, int e) {
+        if (n_out == kRangeCap) {
+            listed += (unsigned long long)(e - out[n_out - 1].y);
+            if (lane == 0) out[n_out - 1].y = e;
+        } else {
+            listed += (unsigned long long)(e - b);
+            if (lane == 0) out[n_out] = make_int2(b, e);
+            n_out++;
+        }
+        __syncwarp();
+    };
+
+    int n = 0;
+    while (n < T.n_nodes) {
+        NodeRec nr = T.nodes[n];
+        bool prune_all = true;
+        if (nr.depth > 0) {
+            const int k = nr.depth;
+            const float* nrm = T.node_normal + (size_t)n * dpad;
+            const float* beta = T.node_beta + nr.beta_off;
+#pragma unroll
+            for (int u = 0; u < QL; u++) {
+                int qi = lane + 32 * u;
+                float d = 0.f;
+                for (int j = 0; j < dpad; j += 4) {
+                    float4 a = *reinterpret_cast<const float4*>(nrm + j);
+                    d = fmaf(a.x, qs[(j + 0) * TQ + qi], d);
+                    d = fmaf(a.y, qs[(j + 1) * TQ + qi], d);
+                    d = fmaf(a.z, qs[(j + 2) * TQ + qi], d);
+                    d = fmaf(a.w, qs[(j + 3) * TQ + qi], d);
+                }
+                if (k <= kMaxLevel) dots[(k - 1) * TQ + qi] = d;
+                float lb = 0.f;
+                int kk = min(k, kMaxLevel);
+                for (int j = 0; j < kk; j++) lb = fmaxf(lb, -(dots[j * TQ + qi] + beta[j]));
+                float safe = lb * 0.9999f - absm[u];
+                bool prune = !valid[u] || ((safe > 0.f) && (safe * safe > thr2[u]));
+                prune_all &= prune;
+            }
+            tests += (unsigned long long)nq_tile;
+        } else {
+            prune_all = false;
+        }
+        prune_all = __all_sync(0xffffffffu, prune_all);
+        if (prune_all) {
+            n += nr.size;
+            continue;
+        }
+        if (nr.leaf >= 0) {
+            if (nr.leaf >= P.leaf_lo && nr.leaf < P.leaf_hi && nr.pos1 > nr.pos0) {
+                int pb = nr.pos0 / kPage, pe = (nr.pos1 + kPage - 1) / kPage;
+                if (cur_b < 0) {
+                    cur_b = pb;
+                    cur_e = pe;
+                } else if (pb <= cur_e) {
+                    cur_e = max(cur_e, pe);
+                } else {
+                    flush(cur_b, cur_e);
+                    cur_b = pb;
+                    cur_e = pe;
+                }
+            }
+        }
+        n += 1;
+    }
+    if (cur_b >= 0) flush(cur_b, cur_e);
+    if (lane == 0) {
+        P.n_ranges[tile] = n_out;
+        if (P.counters) {
+            atomicAdd(&P.counters[4], tests);
+            atomicAdd(&P.counters[5], listed * (unsigned long long)nq_tile);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// merge of per-shard partial lists (sharded-dataset mode): n_lists sorted key lists per query -> final arrays
+// thread per query; lists laid out [n_lists][nq][K].
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_merge_partial(DevTree T, const uint64_t* __restrict__ keys, int n_lists, int nq, int K, int* __restrict__ idx_out,
+                                float* __restrict__ d2_out, float* __restrict__ dist_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int head[16];
+    for (int l = 0; l < n_lists; l++) head[l] = 0;
+    for (int k = 0; k < K; k++) {
+        uint64_t best = ~0ull;
+        int bl = -1;
+        for (int l = 0; l < n_lists; l++) {
+            if (head[l] >= K) continue;
+            uint64_t v = keys[((size_t)l * nq + i) * K + head[l]];
+            if (v < best) { best = v; bl = l; }
+        }
+        int idx = -1;
+        float d2 = 3.402823466e+38f;
+        if (bl >= 0) {
+            head[bl]++;
+            if (best != kEmptyKey) {
+                idx = T.orig_idx[(uint32_t)best & 0x7fffffffu];
+                d2 = __uint_as_float((uint32_t)(best >> 32));
+            }
+        }
+        idx_out[(size_t)i * K + k] = idx;
+        d2_out[(size_t)i * K + k] = d2;
+        if (dist_out) dist_out[(size_t)i * K + k] = __fsqrt_rn(d2);
+    }
+}
+
+}  // namespace scht
