@@ -20,7 +20,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -60,34 +59,50 @@ def make_data(kind, n, dim, nq, seed):
     raise ValueError(kind)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md): one background
+    `nvidia-smi -lms 100` process, parsed when the region ends."""
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
-        super().__init__(daemon=True)
-        self.gpu, self.stop_flag, self.rows = gpu, False, []
+        self.gpu, self.proc, self.path = gpu, None, None
 
-    def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
+            time.sleep(0.5)  # let the first samples land before the timed region starts
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.proc.wait(timeout=5)
             except Exception:
-                pass
-            time.sleep(0.2)
+                self.proc.kill()
 
     def summary(self):
-        if not self.rows:
+        rows = []
+        try:
+            rows = [[x.strip() for x in ln.split(",")] for ln in open(self.path) if ln.count(",") >= 6]
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        # "under load" = samples drawing more than half of the maximum power seen
+        pw = [float(r[2]) if r[2].replace(".", "", 1).isdigit() else 0.0 for r in rows]
+        load = [r for r, p in zip(rows, pw) if p >= 0.5 * max(pw)] or rows
+        sm = sorted(int(r[0]) for r in load if r[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in load)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(rows[0][1]) if rows[0][1].isdigit() else None,
+                "power_w_max": max(pw), "reasons": reasons, "samples": len(rows), "samples_under_load": len(load)}
 
 
 def cpu_reference_sample(data, queries, K, pct, n_sample, cores):
@@ -219,8 +234,7 @@ def main():
     # one extra instrumented step (not part of the timed loop) for the kernel-level numbers
     step_device(st)
     torch.cuda.synchronize()
-    sampler.stop_flag = True
-    sampler.join()
+    sampler.stop()
     stats = st.as_dict()
 
     # end-to-end leg: pinned host buffers through scht_query

@@ -64,7 +64,7 @@ struct scht_handle {
     std::vector<void*> owned;  // device allocations of the tree
     size_t tree_bytes = 0;
     int64_t batch_size = 1000000;  // Code/main.cc:670
-    int scan_variant = 1;
+    int scan_variant = 2;
     std::vector<int> h_leaf_start, h_leaf_count;
     DevBuf q, q_leaf, hist, q_order, state, ranges, n_ranges, idx, d2, dist, counters, leaf_tmp;
 };
@@ -95,21 +95,22 @@ int pick_variant(const scht_handle* h, int K) {
     return -1;
 }
 
-template <int NW, int MINB>
+template <int NW, int MINB, bool FULL>
 int launch_scan_t(scht_handle* h, const ScanParams& P, cudaStream_t s) {
     size_t smem = scan_smem_bytes(NW, P.T.dpad, P.K);
-    CU_TRY(cudaFuncSetAttribute(k_scan<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_scan<NW, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int tq = NW * kQPerWarp;
     int n_tiles = (P.nq + tq - 1) / tq;
-    k_scan<NW, MINB><<<n_tiles, (NW + 1) * 32, smem, s>>>(P);
+    k_scan<NW, MINB, FULL><<<n_tiles, (NW + 1) * 32, smem, s>>>(P);
     CU_TRY(cudaGetLastError());
     return SCHT_OK;
 }
 int launch_scan(scht_handle* h, int variant, const ScanParams& P, cudaStream_t s) {
+    const bool full = (P.T.dpad % kRowsPerStage) == 0;
     switch (variant) {
-        case 0: return launch_scan_t<8, 1>(h, P, s);
-        case 1: return launch_scan_t<7, 2>(h, P, s);
-        default: return launch_scan_t<4, 3>(h, P, s);
+        case 0: return full ? launch_scan_t<8, 1, true>(h, P, s) : launch_scan_t<8, 1, false>(h, P, s);
+        case 1: return full ? launch_scan_t<7, 2, true>(h, P, s) : launch_scan_t<7, 2, false>(h, P, s);
+        default: return full ? launch_scan_t<4, 3, true>(h, P, s) : launch_scan_t<4, 3, false>(h, P, s);
     }
 }
 
@@ -193,7 +194,7 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         // K1 descend + leaf histogram, K3 bucketing
         CU_TRY(cudaMemsetAsync(h->hist.p, 0, (size_t)(T.n_leaves + 1) * 4, s));
         k_descend<<<(nq + 127) / 128, 128, 0, s>>>(T, d_q, nq, h->q_leaf.as<int>(), h->hist.as<int>(), ctr);
-        k_scan_hist<<<1, 1024, 0, s>>>(h->hist.as<int>(), T.n_leaves);
+        k_leaf_prefix_sum<<<1, 1024, 0, s>>>(h->hist.as<int>(), T.n_leaves);
         k_scatter<<<(nq + 255) / 256, 256, 0, s>>>(h->q_leaf.as<int>(), nq, h->hist.as<int>(), h->q_order.as<int>());
         CU_TRY(cudaGetLastError());
         launches += 3;

@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace scht {
 
 constexpr int kPage = 256;         // sorted points per page
@@ -84,6 +86,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Producer-side wait: the producer lane is normally several stages ahead, so it polls with a sleep in between instead
+// of spinning (a spinning lane steals issue slots from the consumer warps that share its scheduler).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
+}
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion counted on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
@@ -106,6 +126,12 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
     uint64_t d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 
@@ -161,7 +187,7 @@ __global__ void k_descend(DevTree T, const float* __restrict__ q, int nq, int* _
 }
 
 // K3a: exclusive scan of the leaf histogram (single CTA; n_leaves is at most a few hundred thousand)
-__global__ void k_scan_hist(int* __restrict__ hist, int n) {
+__global__ void k_leaf_prefix_sum(int* __restrict__ hist, int n) {
     __shared__ int warp_sums[32];
     __shared__ int carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -321,7 +347,8 @@ struct PageWalk {
     }
 };
 
-template <int NW, int MINB>
+// FULL: dpad is a multiple of 16, every stage holds 16 rows and the row loop is straight-line code.
+template <int NW, int MINB, bool FULL>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P) {
     constexpr int TQ = NW * kQPerWarp;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -409,7 +436,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
                 for (int s = 0; s < n_slices; s++, it++) {
                     int st = it % kStages;
                     uint32_t ph = (it / kStages) & 1;
-                    mbar_wait(&empty_bar[st], ph ^ 1);
+                    mbar_wait_backoff(&empty_bar[st], ph ^ 1);
                     int rows = min(kRowsPerStage, dpad - s * kRowsPerStage);
                     uint32_t bytes = (uint32_t)rows * kPage * 4;
                     mbar_arrive_expect_tx(&full_bar[st], bytes);
@@ -439,42 +466,50 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
     uint32_t it = 0;
     while (walk.next(page)) {
         uint64_t acc[kQPerWarp][4];
-#pragma unroll
-        for (int qi = 0; qi < kQPerWarp; qi++)
-#pragma unroll
-            for (int pp = 0; pp < 4; pp++) acc[qi][pp] = 0ull;
 
-        for (int s = 0; s < n_slices; s++, it++) {
+        // one dimension (row of the stage) for the warp's 8 queries x this lane's 8 points.  FIRST: acc = d*d, which
+        // rounds exactly like fma(d, d, +0) and saves zeroing 64 accumulators per page.
+        auto row_step = [&](const float* sp_row, const float* qp_row, auto first) {
+            float4 pa = *reinterpret_cast<const float4*>(sp_row);
+            float4 pb = *reinterpret_cast<const float4*>(sp_row + 128);
+            float4 qa = *reinterpret_cast<const float4*>(qp_row);
+            float4 qb = *reinterpret_cast<const float4*>(qp_row + 4);
+            uint64_t pv[4] = {pack2(pa.x, pa.y), pack2(pa.z, pa.w), pack2(pb.x, pb.y), pack2(pb.z, pb.w)};
+            float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+            for (int qi = 0; qi < kQPerWarp; qi++) {
+                uint64_t qq = pack2(qv[qi], qv[qi]);  // becomes the scalar-broadcast operand form of FADD2
+#pragma unroll
+                for (int pp = 0; pp < 4; pp++) {
+                    uint64_t d = sub2(pv[pp], qq);
+                    acc[qi][pp] = decltype(first)::value ? mul2(d, d) : fma2(d, d, acc[qi][pp]);
+                }
+            }
+        };
+
+        // one stage = one slice of <= 16 dimensions of the page; the first slice starts the accumulators
+        auto stage_step = [&](int s, auto first) {
             int st = it % kStages;
             uint32_t ph = (it / kStages) & 1;
             mbar_wait(&full_bar[st], ph);
             const float* sp = stage_mem + (size_t)st * kRowsPerStage * kPage + 4 * lane;
             const float* qp = qs + (size_t)s * kRowsPerStage * TQ + qw0;
-            int rows = min(kRowsPerStage, dpad - s * kRowsPerStage);
+            row_step(sp, qp, first);
+            if (FULL) {
+#pragma unroll
+                for (int row = 1; row < kRowsPerStage; row++) row_step(sp + row * kPage, qp + row * TQ, std::false_type{});
+            } else {
+                int rows = min(kRowsPerStage, dpad - s * kRowsPerStage);
 #pragma unroll 1
-            for (int row = 0; row < rows; row += 4) {
-#pragma unroll
-                for (int rr = 0; rr < 4; rr++) {
-                    float4 pa = *reinterpret_cast<const float4*>(sp + (row + rr) * kPage);
-                    float4 pb = *reinterpret_cast<const float4*>(sp + (row + rr) * kPage + 128);
-                    float4 qa = *reinterpret_cast<const float4*>(qp + (row + rr) * TQ);
-                    float4 qb = *reinterpret_cast<const float4*>(qp + (row + rr) * TQ + 4);
-                    uint64_t pv[4] = {pack2(pa.x, pa.y), pack2(pa.z, pa.w), pack2(pb.x, pb.y), pack2(pb.z, pb.w)};
-                    float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-#pragma unroll
-                    for (int qi = 0; qi < kQPerWarp; qi++) {
-                        uint64_t qq = pack2(qv[qi], qv[qi]);  // becomes the scalar-broadcast operand form of FADD2
-#pragma unroll
-                        for (int pp = 0; pp < 4; pp++) {
-                            uint64_t d = sub2(pv[pp], qq);
-                            acc[qi][pp] = fma2(d, d, acc[qi][pp]);
-                        }
-                    }
-                }
+                for (int row = 1; row < rows; row++) row_step(sp + row * kPage, qp + row * TQ, std::false_type{});
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[st]);
-        }
+            it++;
+        };
+        stage_step(0, std::true_type{});
+#pragma unroll 1
+        for (int s = 1; s < n_slices; s++) stage_step(s, std::false_type{});
         n_pairs += (unsigned long long)min(kPage, T.n_points - page * kPage);
 
         // ---- candidate filter: anything within the widened K-th distance goes to the exact path ----------
