@@ -126,6 +126,8 @@ typedef struct scht_stats {
     double ms_scan;              /* CUDA-event time of the leaf-scan kernel(s) only */
     int64_t scan_launches;       /* number of leaf-scan kernel launches */
     int64_t kernel_launches;     /* number of kernels launched by the call */
+    int64_t pages_listed;        /* (query,page) pairs the traversal kept for the main scan, x256 ~ candidate points */
+    int64_t prefilter_batches;   /* batches whose main scan used the tensor-core prefilter */
 } scht_stats;
 
 /* Uploads the tree to `device` (CUDA ordinal) in the device layout described in DESIGN.md. */

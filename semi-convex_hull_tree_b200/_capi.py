@@ -37,7 +37,8 @@ class Stats(C.Structure):
     _fields_ = [("n_queries", C.c_int64), ("dist_computations", C.c_int64), ("exact_reevaluations", C.c_int64),
                 ("list_insertions", C.c_int64), ("hyperplane_tests", C.c_int64), ("descent_dists", C.c_int64),
                 ("batches", C.c_int64), ("ms_total", C.c_double), ("ms_device", C.c_double), ("ms_scan", C.c_double),
-                ("scan_launches", C.c_int64), ("kernel_launches", C.c_int64)]
+                ("scan_launches", C.c_int64), ("kernel_launches", C.c_int64), ("pages_listed", C.c_int64),
+                ("prefilter_batches", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -17,6 +17,7 @@
 #include "../../include/scht.h"
 #include "scht_error.h"
 #include "scht_kernels.cuh"
+#include "scht_tc.cuh"
 
 using namespace scht;
 
@@ -65,6 +66,13 @@ struct scht_handle {
     size_t tree_bytes = 0;
     int64_t batch_size = 1000000;  // Code/main.cc:670
     int scan_variant = 2;
+    int tc_mode = 2;              // tensor-core prefilter: 0 off, 1 always, 2 auto (per batch, from the seed bounds)
+    int kp = 0;                   // padded K of the tensor-core page image (0: not built)
+    const float* tcpages = nullptr;
+    const float* d_mean = nullptr;
+    const float* d_pmax = nullptr;
+    float pnorm_max = 0.f;
+    int64_t tc_batches = 0;
     std::vector<int> h_leaf_start, h_leaf_count;
     DevBuf q, q_leaf, hist, q_order, state, ranges, n_ranges, idx, d2, dist, counters, leaf_tmp;
 };
@@ -118,12 +126,16 @@ int launch_traverse(scht_handle* h, const TraverseParams& P, cudaStream_t s) {
     int tq = P.tq;
     int n_tiles = (P.nq + tq - 1) / tq;
     int warps = 4;
-    const int slots = (tq > 32) ? 64 : 32;
+    const int slots = (tq > 64) ? 128 : (tq > 32) ? 64 : 32;
     while (warps > 1 && (int)traverse_smem_bytes(warps, slots, P.T.dpad) > h->max_smem) warps >>= 1;
     size_t smem = traverse_smem_bytes(warps, slots, P.T.dpad);
     if ((int)smem > h->max_smem) return scht::fail(SCHT_ERR_INVALID_ARG, "dimension too large for the traversal kernel");
-    int blocks = (n_tiles + warps - 1) / warps;
-    if (tq > 32) {
+    long long jobs = (long long)n_tiles * P.T.n_cuts;
+    int blocks = (int)((jobs + warps - 1) / warps);
+    if (tq > 64) {
+        CU_TRY(cudaFuncSetAttribute(k_traverse<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_traverse<4><<<blocks, warps * 32, smem, s>>>(P);
+    } else if (tq > 32) {
         CU_TRY(cudaFuncSetAttribute(k_traverse<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_traverse<2><<<blocks, warps * 32, smem, s>>>(P);
     } else {
@@ -173,6 +185,7 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
     P.keys_out = out.keys;
     P.counters = ctr;
     int launches = 0, scans = 0;
+    bool used_tc = false;
 
     if (timed) CU_TRY(cudaEventRecord(h->ev[0], s));
     if (brute) {
@@ -202,7 +215,7 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
 
         CU_TRY(h->state.reserve((size_t)nq * K * 8));
         CU_TRY(h->ranges.reserve((size_t)n_tiles * kRangeCap * sizeof(int2)));
-        CU_TRY(h->n_ranges.reserve((size_t)n_tiles * 4));
+        CU_TRY(h->n_ranges.reserve((size_t)n_tiles * kMaxCuts * 4));
         P.state = h->state.as<uint64_t>();
         P.ranges = h->ranges.as<int2>();
         P.n_ranges = h->n_ranges.as<int>();
@@ -219,6 +232,24 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         launches++;
         scans++;
         if (timed) CU_TRY(cudaEventRecord(h->ev[2], s));
+        // tensor-core prefilter or exact FP32 scan for the main pass?
+        bool use_tc = false;
+        if (h->kp > 0 && h->tc_mode != 0 && (int)tc_smem_bytes(T.dpad, h->kp, K) <= h->max_smem) {
+            if (h->tc_mode == 1) {
+                use_tc = true;
+            } else {
+                k_tc_eligibility<<<(nq + 127) / 128, 128, 0, s>>>(T, d_q, P.q_order, nq, K, P.state, h->d_mean, h->d_pmax, h->pnorm_max, ctr);
+                launches++;
+                unsigned long long ok = 0;
+                CU_TRY(cudaMemcpyAsync(&ok, ctr + 6, 8, cudaMemcpyDeviceToHost, s));
+                CU_TRY(cudaStreamSynchronize(s));
+                use_tc = ok * 10 >= (unsigned long long)nq * 9;  // >= 90 % of the queries have a tight margin
+            }
+        }
+        const int tq_main = use_tc ? kTcQ : tq;
+        const int n_tiles_main = (nq + tq_main - 1) / tq_main;
+        CU_TRY(h->ranges.reserve((size_t)std::max(n_tiles, n_tiles_main) * kRangeCap * sizeof(int2)));
+        P.ranges = h->ranges.as<int2>();
         // K2 traversal with the seed bounds -> page ranges per tile
         TraverseParams TP{};
         TP.T = T;
@@ -227,7 +258,7 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         TP.q_leaf = P.q_leaf;
         TP.nq = nq;
         TP.K = K;
-        TP.tq = tq;
+        TP.tq = tq_main;
         TP.state = P.state;
         TP.ranges = h->ranges.as<int2>();
         TP.n_ranges = h->n_ranges.as<int>();
@@ -241,8 +272,24 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         // K4b main scan
         P.mode = kScanList;
         P.write_mode = partial ? kWriteKeys : kWriteFinal;
-        rc = launch_scan(h, variant, P, s);
-        if (rc) return rc;
+        if (use_tc) {
+            TcScanParams TC{};
+            TC.S = P;
+            TC.tcpages = h->tcpages;
+            TC.mean = h->d_mean;
+            TC.pmax = h->d_pmax;
+            TC.pnorm_max = h->pnorm_max;
+            TC.kp = h->kp;
+            size_t smem = tc_smem_bytes(T.dpad, h->kp, K);
+            CU_TRY(cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_scan_tc<<<n_tiles_main, kTcThreads, smem, s>>>(TC);
+            CU_TRY(cudaGetLastError());
+            h->tc_batches++;
+            used_tc = true;
+        } else {
+            rc = launch_scan(h, variant, P, s);
+            if (rc) return rc;
+        }
         launches++;
         scans++;
         if (timed) CU_TRY(cudaEventRecord(h->ev[4], s));
@@ -260,6 +307,8 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         st->batches += 1;
         st->scan_launches += scans;
         st->kernel_launches += launches;
+        st->pages_listed += (int64_t)c[5];
+        st->prefilter_batches += used_tc ? 1 : 0;
         if (timed) {
             float a = 0, b = 0, c2 = 0;
             CU_TRY(cudaEventElapsedTime(&a, h->ev[0], h->ev[4]));
@@ -426,6 +475,30 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
         memcpy(&lc[(size_t)i * dpad], t->node_left_center + (size_t)i * dim, sizeof(float) * dim);
         memcpy(&rc[(size_t)i * dpad], t->node_right_center + (size_t)i * dim, sizeof(float) * dim);
     }
+    {
+        // subtree jobs of the traversal kernel: the deepest level whose cut (nodes at that depth + shallower leaves) has <= kMaxCuts nodes
+        int d0 = 0;
+        auto count_cuts = [&](int d) {
+            int c = 0;
+            for (int i = 0; i < nn; i++) c += (rec[i].depth == d) || (rec[i].leaf >= 0 && rec[i].depth < d);
+            return c;
+        };
+        while (d0 < depth && count_cuts(d0 + 1) <= kMaxCuts) d0++;
+        std::vector<int> cuts;
+        for (int i = 0; i < nn; i++)
+            if (rec[i].depth == d0 || (rec[i].leaf >= 0 && rec[i].depth < d0)) cuts.push_back(i);
+        std::vector<int> paths(cuts.size() * (size_t)(d0 + 1), -1);
+        for (size_t c = 0; c < cuts.size(); c++) {
+            int n = cuts[c], len = rec[n].depth + 1;
+            for (int i = len - 1; i >= 0; i--) {
+                paths[c * (size_t)(d0 + 1) + i] = n;
+                n = t->node_parent[n];
+            }
+        }
+        T.n_cuts = (int)cuts.size();
+        T.cut_depth = d0;
+        TRY_H(upload(h, paths.data(), paths.size(), &T.cut_path));
+    }
     TRY_H(upload(h, rec.data(), rec.size(), &T.nodes));
     TRY_H(upload(h, t->node_beta, (size_t)t->node_beta_off[nn], &T.node_beta));
     TRY_H(upload(h, nrm.data(), nrm.size(), &T.node_normal));
@@ -473,6 +546,50 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
             CU_H(cudaStreamSynchronize(h->stream));
         }
         tmp.release();
+    }
+    // tensor-core page image (centred, TF32-rounded coordinates + |p'|^2 hi/lo), see scht_tc.cuh
+    if (const char* ev = getenv("SCHT_TC")) h->tc_mode = std::max(0, std::min(2, atoi(ev)));
+    {
+        const int kp = ((dim + 2) + 7) & ~7;
+        const size_t tbytes = (size_t)T.n_pages * kp * kPage * 4;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (h->tc_mode != 0 && kp <= 512 && tbytes < free_b / 2) {
+            std::vector<double> sum(dim, 0.0);
+            for (int64_t i = 0; i < N; i++) {
+                const float* p = t->sorted_points + (size_t)i * dim;
+                for (int j = 0; j < dim; j++) sum[j] += p[j];
+            }
+            std::vector<float> mean(dpad, 0.f), pmax(dpad, 0.f);
+            for (int j = 0; j < dim; j++) mean[j] = (float)(sum[j] / (double)N);
+            double n2max = 0;
+            std::vector<double> amax(dim, 0.0);
+            for (int64_t i = 0; i < N; i++) {
+                const float* p = t->sorted_points + (size_t)i * dim;
+                double s2 = 0;
+                for (int j = 0; j < dim; j++) {
+                    double c = (double)p[j] - (double)mean[j];
+                    amax[j] = std::max(amax[j], std::fabs(c));
+                    s2 += c * c;
+                }
+                n2max = std::max(n2max, s2);
+            }
+            for (int j = 0; j < dim; j++) pmax[j] = (float)(amax[j] * 1.0001);
+            h->pnorm_max = (float)(std::sqrt(n2max) * 1.0001);
+            if (std::isfinite(h->pnorm_max) && h->pnorm_max < 1.0e15f) {
+                TRY_H(upload(h, mean.data(), mean.size(), &h->d_mean));
+                TRY_H(upload(h, pmax.data(), pmax.size(), &h->d_pmax));
+                float* tcp = nullptr;
+                CU_H(cudaMalloc(&tcp, tbytes));
+                h->owned.push_back(tcp);
+                h->tree_bytes += tbytes;
+                const int64_t npos = (int64_t)T.n_pages * kPage;
+                k_build_tcpages<<<(unsigned)((npos + 255) / 256), 256, 0, h->stream>>>(T, h->d_mean, kp, tcp);
+                CU_H(cudaGetLastError());
+                h->tcpages = tcp;
+                h->kp = kp;
+            }
+        }
     }
     CU_H(cudaStreamSynchronize(h->stream));
 #undef TRY_H

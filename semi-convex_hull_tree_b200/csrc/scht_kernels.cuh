@@ -29,8 +29,10 @@ constexpr int kPage = 256;         // sorted points per page
 constexpr int kRowsPerStage = 16;  // dims per shared-memory stage (16 rows x 256 floats = 16 KB)
 constexpr int kStages = 4;
 constexpr int kQPerWarp = 8;       // queries owned by one consumer warp
-constexpr int kMaxLevel = 64;      // constraints beyond this depth are ignored by the pruning bound (still valid)
-constexpr int kRangeCap = 128;     // page ranges per tile; overflow coalesces gaps (scans more, stays exact)
+constexpr int kMaxLevel = 32;      // constraints beyond this depth are ignored by the pruning bound (still valid)
+constexpr int kMaxCuts = 64;       // the traversal of one tile is split into <= 64 subtree jobs (one warp each)
+constexpr int kJobRanges = 8;      // page ranges per (tile, subtree job); overflow coalesces gaps (scans more, stays exact)
+constexpr int kRangeCap = kMaxCuts * kJobRanges;  // range slots per tile
 constexpr uint64_t kEmptyKey = 0x7f7fffffffffffffull;  // FLT_MAX bits (INFINITE, Code/cyw_types.h:18) | all ones
 constexpr float kPadCoord = 3.0e38f;                    // coordinate of padded positions: d2 overflows to +inf
 
@@ -56,6 +58,8 @@ struct DevTree {
     const int* leaf_start;    // [n_leaves]
     const int* leaf_count;    // [n_leaves]
     float xnorm_max;          // max ||x||_2 over the data set (pruning margin)
+    int n_cuts, cut_depth;    // subtree roots the traversal is split at (pre-order), all at depth <= cut_depth
+    const int* cut_path;      // [n_cuts][cut_depth+1] root-side path of each cut node (node ids, -1 padded), cut node last
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -254,8 +258,8 @@ struct ScanParams {
     int mode;
     int write_mode;        // kWriteFinal / kWriteState / kWriteKeys
     int pos_lo, pos_hi;    // only positions in [pos_lo,pos_hi) may enter the lists (sharded-dataset mode)
-    const int2* ranges;    // [n_tiles][kRangeCap] page ranges [x,y) (kScanList)
-    const int* n_ranges;   // [n_tiles]
+    const int2* ranges;    // [n_tiles][kMaxCuts][kJobRanges] page ranges [x,y) (kScanList)
+    const int* n_ranges;   // [n_tiles][kMaxCuts]
     uint64_t* state;       // [nq][K] keys by sorted slot
     uint64_t* keys_out;    // [nq][K] keys by query id (kWriteKeys)
     int* idx_out;          // [nq][K]
@@ -318,24 +322,32 @@ __device__ inline int build_seed_ranges(const int* a0s, const int* a1s, int nq_t
     return n;
 }
 
-// Walks the pages of a tile: the ranges of `list`, minus (optionally) the pages of `seed`.  Producer and consumers
-// run the same walk, so they agree on the stage sequence without communicating.
+// Walks the pages of a tile in ascending order: the ranges of `n_groups` consecutive groups (group g holds cnt[g]
+// ranges at list + g*stride), minus (optionally) the pages of `seed`; a page is never returned twice.  Producer and
+// consumers run the same walk, so they agree on the stage sequence without communicating.
 struct PageWalk {
     const int2* list;
-    int n_list;
+    const int* cnt;
+    int n_groups, stride;
     const int2* seed;
     int n_seed;  // 0: nothing to skip
-    int r, page, sr;
-    __device__ PageWalk(const int2* l, int nl, const int2* s, int ns) : list(l), n_list(nl), seed(s), n_seed(ns), r(0), sr(0) {
-        page = (nl > 0) ? l[0].x : 0;
-    }
+    int g, r, page, sr;
+    __device__ PageWalk(const int2* l, const int* c, int ng, int st, const int2* s, int ns)
+        : list(l), cnt(c), n_groups(ng), stride(st), seed(s), n_seed(ns), g(0), r(0), page(0), sr(0) {}
     __device__ bool next(int& out) {
         for (;;) {
-            while (r < n_list && page >= list[r].y) {
-                r++;
-                if (r < n_list) page = max(page, list[r].x);
+            if (g >= n_groups) return false;
+            if (r >= cnt[g]) {
+                g++;
+                r = 0;
+                continue;
             }
-            if (r >= n_list) return false;
+            const int2 rg = list[(size_t)g * stride + r];
+            if (page < rg.x) page = rg.x;
+            if (page >= rg.y) {
+                r++;
+                continue;
+            }
             while (sr < n_seed && seed[sr].y <= page) sr++;
             if (sr < n_seed && page >= seed[sr].x) {
                 page = seed[sr].y;
@@ -410,21 +422,28 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
 
     // ---- the page list of this tile (identical walk in the producer and in every consumer warp) ------------
     const int n_seed = misc[0];
-    const int2 all_pages = make_int2(0, T.n_pages);
+    if (tid == 0) {
+        misc[1] = 1;  // one range: every page (kScanAll; slot TQ-1 is free there: no seed ranges)
+        if (P.mode == kScanAll) seed_rg[TQ - 1] = make_int2(0, T.n_pages);
+    }
+    __syncthreads();
     const int2* list;
-    int n_list, n_skip = 0;
+    const int* cnt;
+    int n_groups = 1, stride = 0, n_skip = 0;
     if (P.mode == kScanAll) {
-        list = &all_pages;
-        n_list = 1;
+        list = &seed_rg[TQ - 1];
+        cnt = &misc[1];
     } else if (P.mode == kScanSeed) {
         list = seed_rg;
-        n_list = n_seed;
+        cnt = &misc[0];
     } else {
         list = P.ranges + (size_t)tile * kRangeCap;
-        n_list = P.n_ranges[tile];
+        cnt = P.n_ranges + (size_t)tile * kMaxCuts;
+        n_groups = T.n_cuts;
+        stride = kJobRanges;
         n_skip = n_seed;  // pages of the seed scan are already in the lists
     }
-    PageWalk walk(list, n_list, seed_rg, n_skip);
+    PageWalk walk(list, cnt, n_groups, stride, seed_rg, n_skip);
     const int n_slices = (dpad + kRowsPerStage - 1) / kRowsPerStage;
     int page;
 
@@ -634,8 +653,8 @@ struct TraverseParams {
     const int* q_leaf;
     int nq, K, tq;           // tq = queries per tile of the leaf-scan kernel (<= 32*QL)
     const uint64_t* state;   // [nq][K] keys after the seed scan
-    int2* ranges;            // [n_tiles][kRangeCap]
-    int* n_ranges;           // [n_tiles]
+    int2* ranges;            // [n_tiles][kMaxCuts][kJobRanges]
+    int* n_ranges;           // [n_tiles][kMaxCuts]
     int leaf_lo, leaf_hi;    // only leaves in [leaf_lo, leaf_hi) are emitted (sharded-dataset mode)
     unsigned long long* counters;  // [4] node tests (per query), [5] pages listed
 };
@@ -644,16 +663,17 @@ __host__ __device__ inline size_t traverse_smem_bytes(int warps, int tq, int dpa
     return (size_t)warps * ((size_t)dpad * tq * 4 + (size_t)kMaxLevel * tq * 4);
 }
 
-template <int QL>  // queries per lane: tile = 32*QL queries
+template <int QL>  // queries per lane: a tile holds up to 32*QL queries
 __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
     constexpr int TQ = 32 * QL;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const DevTree& T = P.T;
     const int dpad = T.dpad;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int tile = blockIdx.x * nwarps + warp;
     const int n_tiles = (P.nq + P.tq - 1) / P.tq;
-    if (tile >= n_tiles) return;
+    const long long job = (long long)blockIdx.x * nwarps + warp;  // one warp per (tile, subtree job)
+    if (job >= (long long)n_tiles * T.n_cuts) return;
+    const int tile = (int)(job / T.n_cuts), cut = (int)(job % T.n_cuts);
     float* qs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((size_t)dpad * TQ + (size_t)kMaxLevel * TQ);  // [dpad][TQ]
     float* dots = qs + (size_t)dpad * TQ;                                                                            // [level][TQ]
     const int q_begin = tile * P.tq;  // tile stride = the leaf-scan kernel's tile (<= TQ slots used)
@@ -686,13 +706,13 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
     }
     __syncwarp();
 
-    int2* out = P.ranges + (size_t)tile * kRangeCap;
+    int2* out = P.ranges + ((size_t)tile * kMaxCuts + cut) * kJobRanges;
     int n_out = 0, cur_b = -1, cur_e = -1;  // open range [cur_b, cur_e)
     unsigned long long tests = 0, listed = 0;
-    // Append [b,e) (ascending).  When the tile runs out of slots the last range is widened over the gap: the extra
+    // Append [b,e) (ascending).  When the job runs out of slots the last range is widened over the gap: the extra
     // pages only cost time (every scanned pair is evaluated exactly and list insertion is idempotent).
     auto flush = [&](int b, int e) {
-        if (n_out == kRangeCap) {
+        if (n_out == kJobRanges) {
             listed += (unsigned long long)(e - out[n_out - 1].y);
             if (lane == 0) out[n_out - 1].y = e;
         } else {
@@ -702,63 +722,90 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
         }
         __syncwarp();
     };
-
-    int n = 0;
-    while (n < T.n_nodes) {
-        NodeRec nr = T.nodes[n];
+    // Visit one node: memoise the dot of every query with the node's own normal at its level, evaluate the bound
+    // over the node's constraints; true when EVERY query of the tile can skip the subtree.
+    auto visit = [&](int n, const NodeRec& nr) -> bool {
+        if (nr.depth == 0) return false;
         bool prune_all = true;
-        if (nr.depth > 0) {
-            const int k = nr.depth;
-            const float* nrm = T.node_normal + (size_t)n * dpad;
-            const float* beta = T.node_beta + nr.beta_off;
+        const int k = nr.depth;
+        const float* nrm = T.node_normal + (size_t)n * dpad;
+        const float* beta = T.node_beta + nr.beta_off;
 #pragma unroll
-            for (int u = 0; u < QL; u++) {
-                int qi = lane + 32 * u;
-                float d = 0.f;
-                for (int j = 0; j < dpad; j += 4) {
-                    float4 a = *reinterpret_cast<const float4*>(nrm + j);
-                    d = fmaf(a.x, qs[(j + 0) * TQ + qi], d);
-                    d = fmaf(a.y, qs[(j + 1) * TQ + qi], d);
-                    d = fmaf(a.z, qs[(j + 2) * TQ + qi], d);
-                    d = fmaf(a.w, qs[(j + 3) * TQ + qi], d);
-                }
-                if (k <= kMaxLevel) dots[(k - 1) * TQ + qi] = d;
-                float lb = 0.f;
-                int kk = min(k, kMaxLevel);
-                for (int j = 0; j < kk; j++) lb = fmaxf(lb, -(dots[j * TQ + qi] + beta[j]));
-                float safe = lb * 0.9999f - absm[u];
-                bool prune = !valid[u] || ((safe > 0.f) && (safe * safe > thr2[u]));
-                prune_all &= prune;
+        for (int u = 0; u < QL; u++) {
+            int qi = lane + 32 * u;
+            float d0 = 0.f, d1 = 0.f;
+            for (int j = 0; j < dpad; j += 4) {
+                float4 a = *reinterpret_cast<const float4*>(nrm + j);
+                d0 = fmaf(a.x, qs[(j + 0) * TQ + qi], d0);
+                d1 = fmaf(a.y, qs[(j + 1) * TQ + qi], d1);
+                d0 = fmaf(a.z, qs[(j + 2) * TQ + qi], d0);
+                d1 = fmaf(a.w, qs[(j + 3) * TQ + qi], d1);
             }
-            tests += (unsigned long long)nq_tile;
+            const float d = d0 + d1;
+            if (k <= kMaxLevel) dots[(k - 1) * TQ + qi] = d;
+            float lb0 = 0.f, lb1 = 0.f;
+            const int kk = min(k, kMaxLevel);
+            int j = 0;
+            for (; j + 1 < kk; j += 2) {
+                lb0 = fmaxf(lb0, -(dots[j * TQ + qi] + beta[j]));
+                lb1 = fmaxf(lb1, -(dots[(j + 1) * TQ + qi] + beta[j + 1]));
+            }
+            if (j < kk) lb0 = fmaxf(lb0, -(dots[j * TQ + qi] + beta[j]));
+            const float safe = fmaxf(lb0, lb1) * 0.9999f - absm[u];
+            const bool prune = !valid[u] || ((safe > 0.f) && (safe * safe > thr2[u]));
+            prune_all &= prune;
+        }
+        tests += (unsigned long long)nq_tile;
+        return __all_sync(0xffffffffu, prune_all);
+    };
+    auto emit_leaf = [&](const NodeRec& nr) {
+        if (nr.leaf >= P.leaf_lo && nr.leaf < P.leaf_hi && nr.pos1 > nr.pos0) {
+            int pb = nr.pos0 / kPage, pe = (nr.pos1 + kPage - 1) / kPage;
+            if (cur_b < 0) {
+                cur_b = pb;
+                cur_e = pe;
+            } else if (pb <= cur_e) {
+                cur_e = max(cur_e, pe);
+            } else {
+                flush(cur_b, cur_e);
+                cur_b = pb;
+                cur_e = pe;
+            }
+        }
+    };
+
+    // 1. the path root -> cut node (fills the dot memo of the levels above the subtree; any pruned ancestor ends the job)
+    const int* path = T.cut_path + (size_t)cut * (T.cut_depth + 1);
+    int cut_node = 0;
+    bool dead = false;
+    for (int i = 0; i <= T.cut_depth && !dead; i++) {
+        int n = path[i];
+        if (n < 0) break;
+        cut_node = n;
+        dead = visit(n, T.nodes[n]);
+    }
+    // 2. the subtree of the cut node in pre-order (= array order), skipping pruned subtrees
+    if (!dead) {
+        const NodeRec root = T.nodes[cut_node];
+        if (root.leaf >= 0) {
+            emit_leaf(root);
         } else {
-            prune_all = false;
-        }
-        prune_all = __all_sync(0xffffffffu, prune_all);
-        if (prune_all) {
-            n += nr.size;
-            continue;
-        }
-        if (nr.leaf >= 0) {
-            if (nr.leaf >= P.leaf_lo && nr.leaf < P.leaf_hi && nr.pos1 > nr.pos0) {
-                int pb = nr.pos0 / kPage, pe = (nr.pos1 + kPage - 1) / kPage;
-                if (cur_b < 0) {
-                    cur_b = pb;
-                    cur_e = pe;
-                } else if (pb <= cur_e) {
-                    cur_e = max(cur_e, pe);
-                } else {
-                    flush(cur_b, cur_e);
-                    cur_b = pb;
-                    cur_e = pe;
+            int n = cut_node + 1;
+            const int end = cut_node + root.size;
+            while (n < end) {
+                const NodeRec nr = T.nodes[n];
+                if (visit(n, nr)) {
+                    n += nr.size;
+                    continue;
                 }
+                if (nr.leaf >= 0) emit_leaf(nr);
+                n += 1;
             }
         }
-        n += 1;
     }
     if (cur_b >= 0) flush(cur_b, cur_e);
     if (lane == 0) {
-        P.n_ranges[tile] = n_out;
+        P.n_ranges[(size_t)tile * kMaxCuts + cut] = n_out;
         if (P.counters) {
             atomicAdd(&P.counters[4], tests);
             atomicAdd(&P.counters[5], listed * (unsigned long long)nq_tile);

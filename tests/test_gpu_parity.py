@@ -172,5 +172,39 @@ def test_full_size_properties(pkg):
     oi, od2, _, _, _ = orc.knn(ht, q[5000:5200], K, alg=2)
     assert_bit_equal(idx[5000:5200], oi)
     assert_bit_equal(d2[5000:5200], od2)
-    assert st["dist_computations"] <= n * nq
+    assert st["dist_computations"] <= n * nq * 1.05  # the prefilter pass re-reads the seed pages
+    ix.close()
+
+
+@pytest.mark.parametrize("tc", ["0", "1"])
+@pytest.mark.parametrize("n,dim,nq,K,pct,kind", [
+    (60000, 16, 3000, 10, 0.0025, "uniform"),
+    (40000, 32, 1000, 100, 0.005, "gauss"),
+    (30000, 15, 1000, 10, 0.005, "posture"),
+    (20000, 128, 300, 10, 0.01, "sift"),
+    (30000, 3, 1000, 1, 0.002, "uniform"),
+    (3000, 8, 200, 128, 0.05, "uniform"),
+])
+def test_prefilter_on_and_off(pkg, orc, monkeypatch, tc, n, dim, nq, K, pct, kind):
+    """SCHT_TC=1 forces the tensor-core prefilter (even where its margin is useless, e.g. 1e5-scaled data: everything
+    becomes a candidate and must still come out exact); SCHT_TC=0 forces the FP32 scan.  Same bits either way."""
+    monkeypatch.setenv("SCHT_TC", tc)
+    rng = np.random.default_rng(n + dim + K)
+    if kind == "uniform":
+        data, q = rng.random((n, dim), dtype=np.float32), rng.random((nq, dim), dtype=np.float32)
+    elif kind == "gauss":
+        data, q = clusters(rng, n, dim, 50, 0.05), clusters(rng, nq, dim, 50, 0.05)
+    elif kind == "posture":
+        data = clusters(rng, n, dim, 64, 0.05, 1e5)
+        q = data[rng.integers(0, n, nq)].copy()
+    else:
+        data = np.clip(np.rint(clusters(rng, n, dim, 20, 0.1, 100.0)), 0, 218).astype(np.float32)
+        q = np.clip(np.rint(clusters(rng, nq, dim, 20, 0.1, 100.0)), 0, 218).astype(np.float32)
+    ht = pkg.HostTree(data, pct, seed=1)
+    oi, od2, od, _, _ = orc.knn(ht, q, K, alg=2)
+    ix = pkg.Index(ht)
+    idx, d2, d = ix.query(q, K, want_dist=True)
+    assert_bit_equal(idx, oi, "idx")
+    assert_bit_equal(d2, od2, "dist2")
+    assert_bit_equal(d, od, "dist")
     ix.close()
