@@ -66,6 +66,7 @@ struct scht_handle {
     size_t tree_bytes = 0;
     int64_t batch_size = 1000000;  // Code/main.cc:670
     int scan_variant = 2;
+    int traverse_sampling = 1;    // sample the traversal before running it for every tile (SCHT_TRAVERSE_SAMPLING=0 disables)
     int tc_mode = 2;              // tensor-core prefilter: 0 off, 1 always, 2 auto (per batch, from the seed bounds)
     int kp = 0;                   // padded K of the tensor-core page image (0: not built)
     const float* tcpages = nullptr;
@@ -130,7 +131,8 @@ int launch_traverse(scht_handle* h, const TraverseParams& P, cudaStream_t s) {
     while (warps > 1 && (int)traverse_smem_bytes(warps, slots, P.T.dpad) > h->max_smem) warps >>= 1;
     size_t smem = traverse_smem_bytes(warps, slots, P.T.dpad);
     if ((int)smem > h->max_smem) return scht::fail(SCHT_ERR_INVALID_ARG, "dimension too large for the traversal kernel");
-    long long jobs = (long long)n_tiles * P.T.n_cuts;
+    long long jobs = (long long)selection_size(n_tiles, P.sel_mode, P.sel_step) * P.T.n_cuts;
+    if (jobs == 0) return SCHT_OK;
     int blocks = (int)((jobs + warps - 1) / warps);
     if (tq > 64) {
         CU_TRY(cudaFuncSetAttribute(k_traverse<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -166,8 +168,8 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
     CU_TRY(h->q_leaf.reserve((size_t)nq * 4));
     CU_TRY(h->q_order.reserve((size_t)nq * 4));
     CU_TRY(h->hist.reserve((size_t)(T.n_leaves + 1) * 4));
-    CU_TRY(h->counters.reserve(8 * 8));
-    CU_TRY(cudaMemsetAsync(h->counters.p, 0, 64, s));
+    CU_TRY(h->counters.reserve(16 * 8));
+    CU_TRY(cudaMemsetAsync(h->counters.p, 0, 128, s));
     unsigned long long* ctr = h->counters.as<unsigned long long>();
 
     ScanParams P{};
@@ -265,9 +267,40 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         TP.leaf_lo = leaf_lo;
         TP.leaf_hi = leaf_hi;
         TP.counters = ctr;
-        rc = launch_traverse(h, TP, s);
-        if (rc) return rc;
-        launches++;
+        // Sampled first: when the bounds keep >= 90 % of the pages for every 8th tile, they are not evaluated for the
+        // other tiles (all their pages are listed); otherwise the remaining tiles are traversed too.
+        const int kSample = 8;
+        if (n_tiles_main >= 8 * kSample && h->traverse_sampling) {
+            unsigned long long before = 0, after = 0;
+            TP.sel_mode = 1;
+            TP.sel_step = kSample;
+            rc = launch_traverse(h, TP, s);
+            if (rc) return rc;
+            launches++;
+            CU_TRY(cudaMemcpyAsync(&after, ctr + 5, 8, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaStreamSynchronize(s));
+            long long sampled_q = 0;
+            for (int t = 0; t < n_tiles_main; t += kSample) sampled_q += std::min(tq_main, nq - t * tq_main);
+            const int page_lo = P.pos_lo / kPage, page_hi = (P.pos_hi + kPage - 1) / kPage;
+            const double kept = (double)(after - before) / std::max(1.0, (double)sampled_q * std::max(1, page_hi - page_lo));
+            TP.sel_mode = 2;
+            if (kept >= 0.90) {
+                int rest = selection_size(n_tiles_main, 2, kSample);
+                k_list_all<<<(rest + 127) / 128, 128, 0, s>>>(h->ranges.as<int2>(), h->n_ranges.as<int>(), n_tiles_main, T.n_cuts, 2, kSample, page_lo,
+                                                             page_hi);
+                CU_TRY(cudaGetLastError());
+            } else {
+                rc = launch_traverse(h, TP, s);
+                if (rc) return rc;
+            }
+            launches++;
+        } else {
+            TP.sel_mode = 0;
+            TP.sel_step = 1;
+            rc = launch_traverse(h, TP, s);
+            if (rc) return rc;
+            launches++;
+        }
         if (timed) CU_TRY(cudaEventRecord(h->ev[3], s));
         // K4b main scan
         P.mode = kScanList;
@@ -280,11 +313,29 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             TC.pmax = h->d_pmax;
             TC.pnorm_max = h->pnorm_max;
             TC.kp = h->kp;
+#ifdef SCHT_TC_PROF
+            static long long* d_trace = nullptr;
+            if (!d_trace) cudaMalloc(&d_trace, 64 * 8 * 8);
+            cudaMemsetAsync(d_trace, 0, 64 * 8 * 8, s);
+            TC.trace = d_trace;
+#endif
             size_t smem = tc_smem_bytes(T.dpad, h->kp, K);
             CU_TRY(cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_scan_tc<<<n_tiles_main, kTcThreads, smem, s>>>(TC);
             CU_TRY(cudaGetLastError());
             h->tc_batches++;
+#ifdef SCHT_TC_PROF
+            {
+                long long tr[64 * 8];
+                cudaMemcpyAsync(tr, TC.trace, sizeof(tr), cudaMemcpyDeviceToHost, s);
+                cudaStreamSynchronize(s);
+                long long t0 = tr[0];
+                for (int i = 0; i < 40; i++) {
+                    fprintf(stderr, "[trace pg %2d] mma: wait_tempty@%6lld got@%6lld full@%6lld issued@%6lld | epi: wait@%6lld got@%6lld released@%6lld done@%6lld\n", i,
+                            tr[i*8+0]-t0, tr[i*8+1]-t0, tr[i*8+2]-t0, tr[i*8+3]-t0, tr[i*8+4]-t0, tr[i*8+5]-t0, tr[i*8+6]-t0, tr[i*8+7]-t0);
+                }
+            }
+#endif
             used_tc = true;
         } else {
             rc = launch_scan(h, variant, P, s);
@@ -295,9 +346,16 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         if (timed) CU_TRY(cudaEventRecord(h->ev[4], s));
     }
     if (st) {
-        unsigned long long c[8];
-        CU_TRY(cudaMemcpyAsync(c, ctr, 64, cudaMemcpyDeviceToHost, s));
+        unsigned long long c[16];
+        CU_TRY(cudaMemcpyAsync(c, ctr, 128, cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaStreamSynchronize(s));
+#ifdef SCHT_TC_PROF
+        if (used_tc) {
+            double tiles = (double)((nq + kTcQ - 1) / kTcQ);
+            fprintf(stderr, "[tc prof] cycles per tile: producer wait_empty %.0f other %.0f | mma wait_full %.0f wait_tempty %.0f issue %.0f | epi(w0) wait_tfull %.0f work %.0f drain %.0f\n",
+                    c[8] / tiles, c[9] / tiles, c[10] / tiles, c[11] / tiles, c[12] / tiles, c[13] / tiles, c[14] / tiles, c[15] / tiles);
+        }
+#endif
         st->n_queries += nq;
         st->dist_computations += (int64_t)c[0];
         st->exact_reevaluations += (int64_t)c[1];
@@ -548,6 +606,7 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
         tmp.release();
     }
     // tensor-core page image (centred, TF32-rounded coordinates + |p'|^2 hi/lo), see scht_tc.cuh
+    if (const char* ev = getenv("SCHT_TRAVERSE_SAMPLING")) h->traverse_sampling = atoi(ev) != 0;
     if (const char* ev = getenv("SCHT_TC")) h->tc_mode = std::max(0, std::min(2, atoi(ev)));
     {
         const int kp = ((dim + 2) + 7) & ~7;

@@ -656,11 +656,35 @@ struct TraverseParams {
     int2* ranges;            // [n_tiles][kMaxCuts][kJobRanges]
     int* n_ranges;           // [n_tiles][kMaxCuts]
     int leaf_lo, leaf_hi;    // only leaves in [leaf_lo, leaf_hi) are emitted (sharded-dataset mode)
+    int sel_mode, sel_step;  // tile subset: 0 all tiles, 1 tiles with t % step == 0 (sample), 2 the other tiles
     unsigned long long* counters;  // [4] node tests (per query), [5] pages listed
 };
 
 __host__ __device__ inline size_t traverse_smem_bytes(int warps, int tq, int dpad) {
     return (size_t)warps * ((size_t)dpad * tq * 4 + (size_t)kMaxLevel * tq * 4);
+}
+
+// i-th tile of a tile subset (see TraverseParams::sel_mode)
+__host__ __device__ inline int tile_of_selection(int i, int mode, int step) {
+    if (mode == 1) return i * step;
+    if (mode == 2) return i + i / (step - 1) + 1;
+    return i;
+}
+__host__ __device__ inline int selection_size(int n_tiles, int mode, int step) {
+    int sampled = (n_tiles + step - 1) / step;
+    return mode == 1 ? sampled : mode == 2 ? n_tiles - sampled : n_tiles;
+}
+
+// Lists every page of [page_lo, page_hi) for the tiles of a subset (used when a sampled traversal shows that the
+// bounds prune next to nothing: evaluating them for the remaining tiles would cost more than it saves).
+__global__ void k_list_all(int2* __restrict__ ranges, int* __restrict__ n_ranges, int n_tiles, int n_cuts, int mode, int step, int page_lo,
+                           int page_hi) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= selection_size(n_tiles, mode, step)) return;
+    int tile = tile_of_selection(i, mode, step);
+    if (tile >= n_tiles) return;
+    for (int c = 0; c < n_cuts; c++) n_ranges[(size_t)tile * kMaxCuts + c] = (c == 0) ? 1 : 0;
+    ranges[(size_t)tile * kMaxCuts * kJobRanges] = make_int2(page_lo, page_hi);
 }
 
 template <int QL>  // queries per lane: a tile holds up to 32*QL queries
@@ -671,9 +695,10 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
     const int dpad = T.dpad;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int n_tiles = (P.nq + P.tq - 1) / P.tq;
-    const long long job = (long long)blockIdx.x * nwarps + warp;  // one warp per (tile, subtree job)
-    if (job >= (long long)n_tiles * T.n_cuts) return;
-    const int tile = (int)(job / T.n_cuts), cut = (int)(job % T.n_cuts);
+    const long long job = (long long)blockIdx.x * nwarps + warp;  // one warp per (selected tile, subtree job)
+    const int sel = (int)(job / T.n_cuts), cut = (int)(job % T.n_cuts);
+    const int tile = tile_of_selection(sel, P.sel_mode, P.sel_step);
+    if (tile >= n_tiles) return;
     float* qs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((size_t)dpad * TQ + (size_t)kMaxLevel * TQ);  // [dpad][TQ]
     float* dots = qs + (size_t)dpad * TQ;                                                                            // [level][TQ]
     const int q_begin = tile * P.tq;  // tile stride = the leaf-scan kernel's tile (<= TQ slots used)

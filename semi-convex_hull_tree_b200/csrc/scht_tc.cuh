@@ -10,21 +10,32 @@
 // before it may enter the query's top-K list, so results stay bit-identical; the tensor core only decides which of
 // the ~10^11 pairs are worth an exact evaluation (about 1 in 10^4).
 //
-// Roles: warps 0-7 epilogue (warp w reads TMEM lanes 32(w%4)..+31, i.e. thread = query, and columns 128(w/4)..+127 of
-// the page; two warps per scheduler hide the TMEM-load and min-tree latencies), warp 8 = producer lane (cp.async.bulk of
-// page slices already stored in the UMMA K-major no-swizzle layout), warp 9 = MMA issuer.
-// Two 256-column accumulator buffers (all 512 TMEM columns) let the MMA of page i+1 overlap the epilogue of page i.
+// Roles: warps 0-15 epilogue, warp 16 = producer lane (cp.async.bulk of page slices already stored in the UMMA
+// K-major no-swizzle layout), warps 17/18 = MMA issuers.  The unit of the MMA->epilogue pipeline is a HALF page (128
+// points, N=128): the 512 TMEM columns hold four 128-column accumulator buffers.  Group g (MMA warp 17+g and epilogue
+// warps 8g..8g+7) owns half page g of every page and the buffers g and g+2, so two double-buffered chains run
+// interleaved and hide each other's hand-off latencies (measured: a single issuer and 4 epilogue warps spent half their
+// time waiting on each other).  Epilogue warp w reads TMEM lanes 32(w%4)..+31 (thread = query) and 64 of the 128
+// columns of its group's buffer.
 #pragma once
 #include "scht_kernels.cuh"
 
 namespace scht {
 
+#ifdef SCHT_TC_PROF
+#define TCP_T0() long long tcp_t0 = clock64()
+#define TCP_ADD(var) do { long long t1 = clock64(); var += t1 - tcp_t0; tcp_t0 = t1; } while (0)
+#else
+#define TCP_T0()
+#define TCP_ADD(var)
+#endif
+
 constexpr int kTcQ = 128;          // queries per tile (MMA M)
 constexpr int kTcStages = 4;
 constexpr int kTcKSlice = 32;      // K elements per shared-memory stage (32 KB)
-constexpr int kTcEpiWarps = 8;
-constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
-constexpr int kTcQueueCap = 768;   // candidate queue entries per epilogue warp (a 16-column half chunk adds <= 512)
+constexpr int kTcEpiWarps = 16;
+constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;
+constexpr int kTcQueueCap = 384;   // candidate queue entries per epilogue warp (an 8-column quarter chunk adds <= 256)
 
 struct TcScanParams {
     ScanParams S;            // q, q_order, q_leaf, nq, K, write_mode, pos range, ranges (tile = 128 queries), state, outputs
@@ -33,11 +44,12 @@ struct TcScanParams {
     const float* pmax;       // [dpad] max |p_j - mean_j|
     float pnorm_max;         // max |p - mean|_2
     int kp;                  // padded K (multiple of 8) = ceil8(dim + 2)
+    long long* trace;        // debug: [64 pages][8] timestamps of tile 0 (SCHT_TC_PROF builds)
 };
 
 __host__ __device__ inline size_t tc_smem_bytes(int dpad, int kp, int K) {
     size_t b = 1024;                                        // alignment slack
-    b += (size_t)kTcStages * kTcKSlice * kPage * 4;         // B stages (32 KB each)
+    b += (size_t)kTcStages * (kp < kTcKSlice ? kp : kTcKSlice) * kPage * 4;  // B stages (<= 32 KB each)
     b += (size_t)kTcQ * kp * 4;                             // A operand
     b += (size_t)dpad * kTcQ * 4;                           // original queries, dim-major (exact path)
     b += (size_t)kTcQ * K * 8;                              // lists
@@ -67,6 +79,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// One lane of a fully active warp (the lowest), as a warp-uniform predicate: keeps the tcgen05 issue code on the
+// uniform datapath instead of the per-thread ELECT loop the compiler emits inside a divergent `if (lane == 0)`.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\n@px mov.s32 %0, 1;\n}\n"
+        : "+r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -157,20 +178,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     float* stage_mem = reinterpret_cast<float*>(base);                              // [stages][kTcKSlice/4][32][8][4]
-    float* sA = stage_mem + (size_t)kTcStages * kTcKSlice * kPage;                  // [kp/4][16][8][4]
+    const int stage_k = min(kp, kTcKSlice);                                         // K elements held by one stage
+    float* sA = stage_mem + (size_t)kTcStages * stage_k * kPage;                    // [kp/4][16][8][4]
     float* qs = sA + (size_t)kTcQ * kp;                                             // [dpad][128] original queries
     uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)dpad * kTcQ);        // [128][K]
-    uint64_t* queues = lists + (size_t)kTcQ * K;                                    // [8][kTcQueueCap]
+    uint64_t* queues = lists + (size_t)kTcQ * K;                                    // [16][kTcQueueCap]
     int2* seed_rg = reinterpret_cast<int2*>(queues + (size_t)kTcEpiWarps * kTcQueueCap);  // [128]
     int* a0s = reinterpret_cast<int*>(seed_rg + kTcQ);
     int* a1s = a0s + kTcQ;
     int* qids = a1s + kTcQ;
     uint64_t* full_b = reinterpret_cast<uint64_t*>(qids + kTcQ);
     uint64_t* empty_b = full_b + kTcStages;
-    uint64_t* tfull_b = empty_b + kTcStages;   // [2]
-    uint64_t* tempty_b = tfull_b + 2;          // [2]
-    int* qcount = reinterpret_cast<int*>(tempty_b + 2);  // [8]
-    int* qlock = qcount + kTcEpiWarps;                   // [4] one lock per lane quadrant (two warps share its lists)
+    uint64_t* tfull_b = empty_b + kTcStages;   // [4]
+    uint64_t* tempty_b = tfull_b + 4;          // [4]
+    int* qcount = reinterpret_cast<int*>(tempty_b + 4);  // [16]
+    int* qlock = qcount + kTcEpiWarps;                   // [4] one lock per lane quadrant (four warps share its lists)
     int* misc = qlock + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 2);
 
@@ -183,11 +205,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     if (tid == 0) {
         for (int s = 0; s < kTcStages; s++) {
             mbar_init(&full_b[s], 1);
-            mbar_init(&empty_b[s], 1);
+            mbar_init(&empty_b[s], 2);  // one commit per MMA warp
         }
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < 4; b++) {
             mbar_init(&tfull_b[b], 1);
-            mbar_init(&tempty_b[b], kTcEpiWarps);
+            mbar_init(&tempty_b[b], 8);  // the 8 epilogue warps of the buffer's group
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -245,51 +267,99 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
         // ================= producer =================
         if (lane == 0) {
             uint32_t it = 0;
+            [[maybe_unused]] long long w_empty = 0, w_other = 0;
+            TCP_T0();
             while (walk.next(page)) {
                 for (int s = 0; s < n_slices; s++, it++) {
                     int st = it % kTcStages;
                     uint32_t ph = (it / kTcStages) & 1;
+                    TCP_ADD(w_other);
                     mbar_wait_backoff(&empty_b[st], ph ^ 1);
+                    TCP_ADD(w_empty);
                     int kk = min(kTcKSlice, kp - s * kTcKSlice);
                     uint32_t bytes = (uint32_t)kk * kPage * 4;
                     mbar_arrive_expect_tx(&full_b[st], bytes);
-                    bulk_g2s(stage_mem + (size_t)st * kTcKSlice * kPage, TP.tcpages + ((size_t)page * kp + (size_t)s * kTcKSlice) * kPage, bytes,
+                    bulk_g2s(stage_mem + (size_t)st * stage_k * kPage, TP.tcpages + ((size_t)page * kp + (size_t)s * kTcKSlice) * kPage, bytes,
                              &full_b[st]);
                 }
             }
+#ifdef SCHT_TC_PROF
+            atomicAdd(&P.counters[8], (unsigned long long)w_empty);
+            atomicAdd(&P.counters[9], (unsigned long long)w_other);
+#endif
         }
-    } else if (warp == kTcEpiWarps + 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPage >> 3) << 17) | ((uint32_t)(kTcQ >> 4) << 24);
-            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(stage_mem);
+    } else if (warp > kTcEpiWarps) {
+        // ================= MMA issuers: warp 17+g issues the MMAs of half page g; the whole warp walks the pipeline,
+        // one elected lane issues (keeps tcgen05 on the uniform datapath) =================
+        {
+            const int g = warp - (kTcEpiWarps + 1);
+            constexpr int kHalf = kPage / 2;  // N of one MMA: a half page
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kHalf >> 3) << 17) | ((uint32_t)(kTcQ >> 4) << 24);
+            // Descriptors are affine in (slice, k8, stage): two bases built once plus 16-byte-unit offsets.
+            constexpr uint32_t kAStep = 2 * (kTcQ / 8) * 128 / 16;   // two K chunks of the A image, in 16-byte units
+            constexpr uint32_t kBStep = 2 * (kPage / 8) * 128 / 16;  // two K chunks of a B stage
+            constexpr uint32_t kBHalf = (kHalf / 8) * 128 / 16;      // second half page inside a K chunk
+            const uint32_t kBStage = (uint32_t)stage_k * kPage * 4 / 16;
+            const uint64_t da0 = umma_desc_kmajor(smem_u32(sA), (kTcQ / 8) * 128, 128);
+            const uint64_t db0 = umma_desc_kmajor(smem_u32(stage_mem), (kPage / 8) * 128, 128) + (uint64_t)((uint32_t)g * kBHalf);
             uint32_t it = 0, pg = 0;
+            [[maybe_unused]] long long m_full = 0, m_tempty = 0, m_issue = 0;
+            TCP_T0();
             while (walk.next(page)) {
-                const uint32_t buf = pg & 1;
+                // half page g of page pg -> buffer 2*(pg&1)+g, used for the (pg>>1)-th time
+                const uint32_t buf = 2 * (pg & 1) + g;
+                const uint32_t d_tmem = tmem + buf * kHalf;
+                TCP_ADD(m_issue);
+#ifdef SCHT_TC_PROF
+                const bool tr = TP.trace && tile == 0 && g == 0 && lane == 0 && pg >= 2000 && pg < 2064;
+                if (tr) TP.trace[(pg - 2000) * 8 + 0] = clock64();
+#endif
                 mbar_wait(&tempty_b[buf], ((pg >> 1) & 1) ^ 1);
-                tc_fence_after();
+#ifdef SCHT_TC_PROF
+                if (tr) TP.trace[(pg - 2000) * 8 + 1] = clock64();
+#endif
+                TCP_ADD(m_tempty);
                 for (int s = 0; s < n_slices; s++, it++) {
-                    int st = it % kTcStages;
-                    uint32_t ph = (it / kTcStages) & 1;
+                    const uint32_t st = it % kTcStages;
+                    const uint32_t ph = (it / kTcStages) & 1;
+                    TCP_ADD(m_issue);
                     mbar_wait(&full_b[st], ph);
+#ifdef SCHT_TC_PROF
+                    if (tr) TP.trace[(pg - 2000) * 8 + 2] = clock64();
+#endif
+                    TCP_ADD(m_full);
                     tc_fence_after();
-                    int kk = min(kTcKSlice, kp - s * kTcKSlice);
-                    for (int k8 = 0; k8 < kk / 8; k8++) {
-                        // 2 core-matrix columns (16 B each) per MMA; LBO = distance between them, SBO = next 8-row group
-                        uint64_t da = umma_desc_kmajor(a_base + (uint32_t)(s * (kTcKSlice / 4) + k8 * 2) * (kTcQ / 8) * 128, (kTcQ / 8) * 128, 128);
-                        uint64_t db = umma_desc_kmajor(b_base + (uint32_t)st * kTcKSlice * kPage * 4 + (uint32_t)(k8 * 2) * (kPage / 8) * 128,
-                                                       (kPage / 8) * 128, 128);
-                        umma_tf32(tmem + buf * kPage, da, db, idesc, (s > 0 || k8 > 0) ? 1u : 0u);
+                    const int n8 = min(kTcKSlice, kp - s * kTcKSlice) / 8;
+                    const uint64_t da_s = da0 + (uint64_t)((uint32_t)s * (kTcKSlice / 8) * kAStep);
+                    const uint64_t db_s = db0 + (uint64_t)(st * kBStage);
+                    if (elect_one_sync()) {
+#pragma unroll 4
+                        for (int k8 = 0; k8 < n8; k8++)
+                            umma_tf32(d_tmem, da_s + (uint64_t)((uint32_t)k8 * kAStep), db_s + (uint64_t)((uint32_t)k8 * kBStep), idesc,
+                                      (s > 0 || k8 > 0) ? 1u : 0u);
+                        if (s == n_slices - 1) umma_commit(&tfull_b[buf]);
+                        umma_commit(&empty_b[st]);  // the stage may be refilled once both issuers' MMAs have read it
                     }
-                    umma_commit(&empty_b[st]);  // the stage may be refilled once these MMAs have read it
+                    __syncwarp();
+#ifdef SCHT_TC_PROF
+                    if (tr) TP.trace[(pg - 2000) * 8 + 3] = clock64();
+#endif
                 }
-                umma_commit(&tfull_b[buf]);
                 pg++;
             }
+#ifdef SCHT_TC_PROF
+            if (lane == 0 && g == 0) {
+                atomicAdd(&P.counters[10], (unsigned long long)m_full);
+                atomicAdd(&P.counters[11], (unsigned long long)m_tempty);
+                atomicAdd(&P.counters[12], (unsigned long long)m_issue);
+            }
+#endif
         }
     } else {
         // ================= epilogue: thread = query (TMEM lane), this warp's 128 columns of every page =================
-        const int quad = warp & 3, half = warp >> 2;
+        // quad = TMEM lane quadrant (= warp id % 4, a hardware rule), sub = which 64 columns of the buffer,
+        // half = pipeline group = which half page of every page
+        const int quad = warp & 3, sub = (warp >> 2) & 1, half = warp >> 3;
         const int qi = quad * 32 + lane;  // tile-local query
         uint64_t* myq = queues + (size_t)warp * kTcQueueCap;
         int* mycount = &qcount[warp];
@@ -313,10 +383,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
         unsigned int n_exact = 0, n_ins = 0;
 
         // Exact re-evaluation of the queued candidates (reference arithmetic, 32 at a time) and insertion into the lists.
-        // The two warps of a lane quadrant share the 32 lists, so the insert phase runs under the quadrant's lock.
-        auto drain = [&]() {
+        // The four warps of a lane quadrant share the 32 lists, so the insert phase runs under the quadrant's lock.
+        auto drain = [&](int n) {
             __syncwarp();
-            const int n = *mycount;
             for (int b0 = 0; b0 < n; b0 += 32) {
                 bool cand = false;
                 float d2 = 0.f;
@@ -364,7 +433,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
             __syncwarp();
         };
 
-        // balanced min tree over 32 accumulator values (FMNMX3, depth 4) and the rare push path
+        // Balanced min tree over 32 accumulator values (FMNMX3, depth 4).  Rare path (some lane has a value under its
+        // bound): each such lane builds the bit mask of its surviving columns, reserves that many queue slots with ONE
+        // shared-memory atomic and writes them; lanes without a hit only wait at the reconvergence point.
         auto process = [&](const uint32_t (&v)[32], int col0) {
             float m[11];
 #pragma unroll
@@ -375,56 +446,104 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
             const float mn = fminf(fminf(fminf(n0, n1), n2), n3);
             const bool hit = mn <= Tq;
             if (__any_sync(0xffffffffu, hit)) {
+                uint32_t mask = 0;
+                if (hit) {
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    if (*mycount > kTcQueueCap - 512) drain();  // warp-uniform: only this warp changes its counter
-                    if (hit) {
-#pragma unroll
-                        for (int c = 16 * h; c < 16 * h + 16; c++) {
-                            if (__uint_as_float(v[c]) <= Tq) {
-                                int slot = atomicAdd(mycount, 1);
-                                myq[slot] = ((uint64_t)(uint32_t)lane << 32) | (uint32_t)(page * kPage + col0 + c);
+                    for (int c = 0; c < 32; c++) mask |= (__uint_as_float(v[c]) <= Tq ? 1u : 0u) << c;
+                }
+                for (;;) {
+                    bool fits = true;
+                    int slot = 0;
+                    const int cnt = __popc(mask);
+                    if (cnt) {
+                        slot = atomicAdd(mycount, cnt);
+                        fits = slot + cnt <= kTcQueueCap;
+                        if (fits) {
+                            while (mask) {
+                                const int c = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                myq[slot++] = ((uint64_t)(uint32_t)lane << 32) | (uint32_t)(page * kPage + col0 + c);
                             }
                         }
                     }
                     __syncwarp();
+                    if (!__any_sync(0xffffffffu, !fits)) break;
+                    // queue overflow (only while bounds are still loose): reservations are made in slot order, so the
+                    // entries below the first failed reservation are complete; drain them, then the failed lanes retry
+                    int first_bad = fits ? 0x7fffffff : slot;
+                    for (int o = 16; o; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
+                    drain(first_bad);
+                    if (fits) mask = 0;
+                    if (mask) {
+                        // the bound may have tightened: drop survivors that no longer pass
+                        uint32_t keep = 0;
+#pragma unroll
+                        for (int c = 0; c < 32; c++) keep |= (__uint_as_float(v[c]) <= Tq ? 1u : 0u) << c;
+                        mask &= keep;
+                    }
                 }
             }
         };
 
         uint32_t pg = 0;
+        [[maybe_unused]] long long e_wait = 0, e_work = 0, e_drain = 0;
+        TCP_T0();
         while (walk.next(page)) {
-            const uint32_t buf = pg & 1;
+            const uint32_t buf = 2 * (pg & 1) + half;
+            TCP_ADD(e_work);
+#ifdef SCHT_TC_PROF
+            const bool tr = TP.trace && tile == 0 && warp == 0 && lane == 0 && pg >= 2000 && pg < 2064;
+            if (tr) TP.trace[(pg - 2000) * 8 + 4] = clock64();
+#endif
             mbar_wait(&tfull_b[buf], (pg >> 1) & 1);
+#ifdef SCHT_TC_PROF
+            if (tr) TP.trace[(pg - 2000) * 8 + 5] = clock64();
+#endif
+            TCP_ADD(e_wait);
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + buf * kPage + half * 128;
-            uint32_t va[32], vb[32];
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + buf * 128 + sub * 64;
+            const int col0 = half * 128 + sub * 64;
+            // (four epilogue warps per scheduler hide the TMEM-load latency; one 32-column register buffer keeps the
+            // kernel inside the 96-register budget of a 608-thread CTA)
+            uint32_t va[32];
             tmem_ld32(taddr, va);
             tmem_ld_wait();
-            tmem_ld32(taddr + 32, vb);
-            process(va, half * 128);
-            tmem_ld_wait();
-            tmem_ld32(taddr + 64, va);
-            process(vb, half * 128 + 32);
-            tmem_ld_wait();
-            tmem_ld32(taddr + 96, vb);
-            process(va, half * 128 + 64);
+            process(va, col0);
+            tmem_ld32(taddr + 32, va);
             tmem_ld_wait();
             // all of this warp's TMEM reads of the buffer are complete: hand it back to the MMA issuer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_b[buf]);
-            process(vb, half * 128 + 96);
-            if (half == 0) n_pairs += (unsigned long long)min(kPage, T.n_points - page * kPage);
-            if (*mycount >= 128) drain();
+#ifdef SCHT_TC_PROF
+            if (tr) TP.trace[(pg - 2000) * 8 + 6] = clock64();
+#endif
+            process(va, col0 + 32);
+#ifdef SCHT_TC_PROF
+            if (tr) TP.trace[(pg - 2000) * 8 + 7] = clock64();
+#endif
+            if (half == 0 && sub == 0) n_pairs += (unsigned long long)min(kPage, T.n_points - page * kPage);
+            TCP_ADD(e_work);
+            {
+                const int qn = *reinterpret_cast<volatile int*>(mycount);  // warp-uniform: only this warp changes it
+                if (qn >= 128) drain(qn);
+            }
+            TCP_ADD(e_drain);
             pg++;
         }
-        drain();
-        // both warps of the quadrant must be done before the lists are final
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        drain(*reinterpret_cast<volatile int*>(mycount));
+#ifdef SCHT_TC_PROF
+        if (lane == 0 && warp == 0) {
+            atomicAdd(&P.counters[13], (unsigned long long)e_wait);
+            atomicAdd(&P.counters[14], (unsigned long long)e_work);
+            atomicAdd(&P.counters[15], (unsigned long long)e_drain);
+        }
+#endif
+        // all four warps of the quadrant must be done before the lists are final
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
 
         // ---- results: the first warp of each quadrant writes its 32 queries ----
-        if (half == 0) {
+        if (half == 0 && sub == 0) {
             for (int qq = 0; qq < 32; qq++) {
                 const int ql = quad * 32 + qq;
                 if (ql >= nq_tile) break;
