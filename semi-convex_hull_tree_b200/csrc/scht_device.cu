@@ -69,7 +69,8 @@ struct scht_handle {
     int traverse_sampling = 1;    // sample the traversal before running it for every tile (SCHT_TRAVERSE_SAMPLING=0 disables)
     int tc_mode = 2;              // tensor-core prefilter: 0 off, 1 always, 2 auto (per batch, from the seed bounds)
     int kp = 0;                   // padded K of the tensor-core page image (0: not built)
-    const float* tcpages = nullptr;
+    const unsigned char* tcpages = nullptr;
+    float tc_scale = 1.f, pabs_sum = 0.f, norm_unit = 1.f;
     const float* d_mean = nullptr;
     const float* d_pmax = nullptr;
     float pnorm_max = 0.f;
@@ -240,7 +241,8 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             if (h->tc_mode == 1) {
                 use_tc = true;
             } else {
-                k_tc_eligibility<<<(nq + 127) / 128, 128, 0, s>>>(T, d_q, P.q_order, nq, K, P.state, h->d_mean, h->d_pmax, h->pnorm_max, ctr);
+                k_tc_eligibility<<<(nq + 127) / 128, 128, 0, s>>>(T, d_q, P.q_order, nq, K, P.state, h->d_mean, h->d_pmax, h->pnorm_max, h->pabs_sum,
+                                                                  h->tc_scale, ctr);
                 launches++;
                 unsigned long long ok = 0;
                 CU_TRY(cudaMemcpyAsync(&ok, ctr + 6, 8, cudaMemcpyDeviceToHost, s));
@@ -312,30 +314,15 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             TC.mean = h->d_mean;
             TC.pmax = h->d_pmax;
             TC.pnorm_max = h->pnorm_max;
+            TC.pabs_sum = h->pabs_sum;
+            TC.scale = h->tc_scale;
+            TC.norm_unit = h->norm_unit;
             TC.kp = h->kp;
-#ifdef SCHT_TC_PROF
-            static long long* d_trace = nullptr;
-            if (!d_trace) cudaMalloc(&d_trace, 64 * 8 * 8);
-            cudaMemsetAsync(d_trace, 0, 64 * 8 * 8, s);
-            TC.trace = d_trace;
-#endif
             size_t smem = tc_smem_bytes(T.dpad, h->kp, K);
             CU_TRY(cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_scan_tc<<<n_tiles_main, kTcThreads, smem, s>>>(TC);
             CU_TRY(cudaGetLastError());
             h->tc_batches++;
-#ifdef SCHT_TC_PROF
-            {
-                long long tr[64 * 8];
-                cudaMemcpyAsync(tr, TC.trace, sizeof(tr), cudaMemcpyDeviceToHost, s);
-                cudaStreamSynchronize(s);
-                long long t0 = tr[0];
-                for (int i = 0; i < 40; i++) {
-                    fprintf(stderr, "[trace pg %2d] mma: wait_tempty@%6lld got@%6lld full@%6lld issued@%6lld | epi: wait@%6lld got@%6lld released@%6lld done@%6lld\n", i,
-                            tr[i*8+0]-t0, tr[i*8+1]-t0, tr[i*8+2]-t0, tr[i*8+3]-t0, tr[i*8+4]-t0, tr[i*8+5]-t0, tr[i*8+6]-t0, tr[i*8+7]-t0);
-                }
-            }
-#endif
             used_tc = true;
         } else {
             rc = launch_scan(h, variant, P, s);
@@ -349,13 +336,6 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         unsigned long long c[16];
         CU_TRY(cudaMemcpyAsync(c, ctr, 128, cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaStreamSynchronize(s));
-#ifdef SCHT_TC_PROF
-        if (used_tc) {
-            double tiles = (double)((nq + kTcQ - 1) / kTcQ);
-            fprintf(stderr, "[tc prof] cycles per tile: producer wait_empty %.0f other %.0f | mma wait_full %.0f wait_tempty %.0f issue %.0f | epi(w0) wait_tfull %.0f work %.0f drain %.0f\n",
-                    c[8] / tiles, c[9] / tiles, c[10] / tiles, c[11] / tiles, c[12] / tiles, c[13] / tiles, c[14] / tiles, c[15] / tiles);
-        }
-#endif
         st->n_queries += nq;
         st->dist_computations += (int64_t)c[0];
         st->exact_reevaluations += (int64_t)c[1];
@@ -609,11 +589,11 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     if (const char* ev = getenv("SCHT_TRAVERSE_SAMPLING")) h->traverse_sampling = atoi(ev) != 0;
     if (const char* ev = getenv("SCHT_TC")) h->tc_mode = std::max(0, std::min(2, atoi(ev)));
     {
-        const int kp = ((dim + 2) + 7) & ~7;
-        const size_t tbytes = (size_t)T.n_pages * kp * kPage * 4;
+        const int kp = (dim + 3 + 15) & ~15;
+        const size_t tbytes = (size_t)T.n_pages * tc_page_bytes(kp);
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        if (h->tc_mode != 0 && kp <= 512 && tbytes < free_b / 2) {
+        if (h->tc_mode != 0 && kp <= 1024 && tbytes < free_b / 2) {
             std::vector<double> sum(dim, 0.0);
             for (int64_t i = 0; i < N; i++) {
                 const float* p = t->sorted_points + (size_t)i * dim;
@@ -633,17 +613,28 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
                 }
                 n2max = std::max(n2max, s2);
             }
-            for (int j = 0; j < dim; j++) pmax[j] = (float)(amax[j] * 1.0001);
+            double amax_all = 0, asum = 0;
+            for (int j = 0; j < dim; j++) {
+                pmax[j] = (float)(amax[j] * 1.0001);
+                amax_all = std::max(amax_all, amax[j]);
+                asum += amax[j];
+            }
             h->pnorm_max = (float)(std::sqrt(n2max) * 1.0001);
-            if (std::isfinite(h->pnorm_max) && h->pnorm_max < 1.0e15f) {
+            h->pabs_sum = (float)(asum * 1.0001);
+            // power-of-two scale that puts the largest centred coordinate into (128, 256]: well inside FP16's range
+            h->tc_scale = (amax_all > 0 && std::isfinite(amax_all)) ? (float)std::exp2(std::floor(std::log2(256.0 / amax_all))) : 1.f;
+            const double sn = (double)h->tc_scale * h->tc_scale * n2max;
+            // norm slots hold s^2|p'|^2 / u with u a power of two that keeps them below 16384 (FP16 range, room for 60000 on padding)
+            h->norm_unit = (sn > 16384.0) ? (float)std::exp2(std::ceil(std::log2(sn / 16384.0))) : 1.f;
+            if (std::isfinite(h->pnorm_max) && std::isfinite(h->tc_scale) && h->tc_scale > 1e-30f && h->tc_scale < 1e30f && sn < 1e37) {
                 TRY_H(upload(h, mean.data(), mean.size(), &h->d_mean));
                 TRY_H(upload(h, pmax.data(), pmax.size(), &h->d_pmax));
-                float* tcp = nullptr;
+                unsigned char* tcp = nullptr;
                 CU_H(cudaMalloc(&tcp, tbytes));
                 h->owned.push_back(tcp);
                 h->tree_bytes += tbytes;
                 const int64_t npos = (int64_t)T.n_pages * kPage;
-                k_build_tcpages<<<(unsigned)((npos + 255) / 256), 256, 0, h->stream>>>(T, h->d_mean, kp, tcp);
+                k_build_tcpages<<<(unsigned)((npos + 255) / 256), 256, 0, h->stream>>>(T, h->d_mean, h->tc_scale, h->norm_unit, kp, tcp);
                 CU_H(cudaGetLastError());
                 h->tcpages = tcp;
                 h->kp = kp;

@@ -1,68 +1,62 @@
 // Tensor-core prefilter for the leaf scan (north_star: "Tensor cores are allowed only as a TF32 or BF16 GEMM-form
 // prefilter followed by exact FP32 rescoring").
 //
-// For a tile of 128 queries and a page of 256 points one tcgen05.mma chain (kind::tf32, M=128, N=256, accumulator in
-// TMEM) evaluates   S[q][p] = -2 q'.p' + |p'|^2   with q' = q - mean, p' = p - mean (operands rounded to TF32,
-// |p'|^2 carried as a hi+lo pair in two extra K slots).  |p-q|^2 = S + |q'|^2 up to a rounding error that is bounded
-// per query (margin_q, DESIGN.md section "Tensor-core prefilter").  A pair survives the filter when
-//         S <= kth_q * (1 + 2^-20) - |q'|^2 + margin_q
+// For a tile of 128 queries and a page of 256 points a tcgen05.mma chain (kind::f16, FP16 operands -- the same 11-bit
+// significand as TF32 at half the bytes -- FP32 accumulator in TMEM) evaluates
+//     S[q][p] = -2 s^2 q'.p' + s^2 |p'|^2 = s^2 (|p-q|^2 - |q'|^2)
+// with q' = q - mean, p' = p - mean and s a power of two that puts the data into FP16's range; the norm rides in three
+// extra K slots as an exact hi+mid+lo FP16 split (33 bits) against a constant in the query operand, so the epilogue
+// is a pure min tree over the accumulator.  The rounding error of S is bounded per query (margin_q, DESIGN.md
+// "Tensor-core prefilter").  A pair survives when
+//         S <= s^2 (kth_q (1 + 2^-20) - |q'|^2 + margin_q)
 // and every survivor is re-evaluated with the reference's float/double arithmetic (the same exact path as k_scan)
 // before it may enter the query's top-K list, so results stay bit-identical; the tensor core only decides which of
-// the ~10^11 pairs are worth an exact evaluation (about 1 in 10^4).
+// the ~10^11 pairs are worth an exact evaluation (about 3 in 10^4).
 //
 // Roles: warps 0-15 epilogue, warp 16 = producer lane (cp.async.bulk of page slices already stored in the UMMA
 // K-major no-swizzle layout), warps 17/18 = MMA issuers.  The unit of the MMA->epilogue pipeline is a HALF page (128
 // points, N=128): the 512 TMEM columns hold four 128-column accumulator buffers.  Group g (MMA warp 17+g and epilogue
 // warps 8g..8g+7) owns half page g of every page and the buffers g and g+2, so two double-buffered chains run
-// interleaved and hide each other's hand-off latencies (measured: a single issuer and 4 epilogue warps spent half their
-// time waiting on each other).  Epilogue warp w reads TMEM lanes 32(w%4)..+31 (thread = query) and 64 of the 128
-// columns of its group's buffer.
+// interleaved and hide each other's hand-off latencies.  Epilogue warp w reads TMEM lanes 32(w%4)..+31 (thread =
+// query) and 64 of the 128 columns of its group's buffer.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "scht_kernels.cuh"
 
 namespace scht {
 
-#ifdef SCHT_TC_PROF
-#define TCP_T0() long long tcp_t0 = clock64()
-#define TCP_ADD(var) do { long long t1 = clock64(); var += t1 - tcp_t0; tcp_t0 = t1; } while (0)
-#else
-#define TCP_T0()
-#define TCP_ADD(var)
-#endif
-
 constexpr int kTcQ = 128;          // queries per tile (MMA M)
-constexpr int kTcStages = 4;
-constexpr int kTcKSlice = 32;      // K elements per shared-memory stage (32 KB)
+constexpr int kTcKSlice = 32;      // K elements (FP16) per shared-memory stage: 16 KB
+constexpr int kTcStages = 6;       // slice stages
 constexpr int kTcEpiWarps = 16;
 constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;
-constexpr int kTcQueueCap = 384;   // candidate queue entries per epilogue warp (an 8-column quarter chunk adds <= 256)
+constexpr int kTcQueueCap = 384;   // candidate queue entries per epilogue warp
 
 struct TcScanParams {
     ScanParams S;            // q, q_order, q_leaf, nq, K, write_mode, pos range, ranges (tile = 128 queries), state, outputs
-    const float* tcpages;    // [n_pages][kp/4][32][8][4]  tf32-rounded centred coordinates + norm hi/lo
+    const unsigned char* tcpages;  // per page: FP16 image [kp/8][32][8][8] (kp*512 B): s p'_j, then norm hi/mid/lo
     const float* mean;       // [dpad]
     const float* pmax;       // [dpad] max |p_j - mean_j|
     float pnorm_max;         // max |p - mean|_2
-    int kp;                  // padded K (multiple of 8) = ceil8(dim + 2)
-    long long* trace;        // debug: [64 pages][8] timestamps of tile 0 (SCHT_TC_PROF builds)
+    float pabs_sum;          // sum_j pmax_j
+    float scale;             // s (power of two)
+    float norm_unit;         // power of two u: the norm slots hold s^2|p'|^2 / u, the query operand holds u
+    int kp;                  // padded K (multiple of 16) = ceil16(dim + 3)
 };
 
-__host__ __device__ inline size_t tc_smem_bytes(int dpad, int kp, int K) {
-    size_t b = 1024;                                        // alignment slack
-    b += (size_t)kTcStages * (kp < kTcKSlice ? kp : kTcKSlice) * kPage * 4;  // B stages (<= 32 KB each)
-    b += (size_t)kTcQ * kp * 4;                             // A operand
-    b += (size_t)dpad * kTcQ * 4;                           // original queries, dim-major (exact path)
-    b += (size_t)kTcQ * K * 8;                              // lists
-    b += (size_t)kTcEpiWarps * kTcQueueCap * 8;             // candidate queues
-    b += (size_t)kTcQ * 8 + (size_t)kTcQ * 3 * 4;           // seed ranges, a0, a1, qid
-    b += 256;                                               // barriers, counters, tmem base
-    return b;
-}
+__host__ __device__ inline size_t tc_page_bytes(int kp) { return (size_t)kp * 512; }
 
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+__host__ __device__ inline size_t tc_smem_bytes(int dpad, int kp, int K) {
+    size_t b = 1024;                                                         // alignment slack
+    b += (size_t)kTcStages * (kp < kTcKSlice ? kp : kTcKSlice) * 512;        // B slice stages (<= 16 KB each)
+    b += (size_t)kTcQ * kp * 2;                                              // A operand
+    b += (size_t)dpad * kTcQ * 4;                                            // original queries, dim-major (exact path)
+    b += (size_t)kTcQ * K * 8;                                               // lists
+    b += (size_t)kTcEpiWarps * kTcQueueCap * 8;                              // candidate queues
+    b += (size_t)kTcQ * 3 * 4;                                               // a0, a1, qid
+    b += 512;                                                                // barriers, counters, tmem base
+    return b;
 }
 
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -73,10 +67,10 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lb
     d |= (uint64_t)1 << 46;  // Blackwell descriptor version; no swizzle, base offset 0
     return d;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -84,9 +78,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 // uniform datapath instead of the per-thread ELECT loop the compiler emits inside a divergent `if (lane == 0)`.
 __device__ __forceinline__ bool elect_one_sync() {
     uint32_t pred = 0;
-    asm volatile(
-        "{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\n@px mov.s32 %0, 1;\n}\n"
-        : "+r"(pred));
+    asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred));
     return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -109,60 +101,64 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // -------------------------------------------------------------------------------------------------------------
 // builder of the tensor-core page image from the exact dim-major pages (one thread per sorted position)
 // -------------------------------------------------------------------------------------------------------------
-__global__ void k_build_tcpages(DevTree T, const float* __restrict__ mean, int kp, float* __restrict__ tcpages) {
+__global__ void k_build_tcpages(DevTree T, const float* __restrict__ mean, float scale, float norm_unit, int kp,
+                                unsigned char* __restrict__ tcpages) {
     int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= (int64_t)T.n_pages * kPage) return;
-    int page = (int)(pos / kPage), in_page = (int)(pos % kPage);
-    const float* src = T.pages + (size_t)page * T.dpad * kPage + in_page;
-    float* dst = tcpages + (size_t)page * kp * kPage;
-    const int g = in_page >> 3, r = in_page & 7;
+    int page = (int)(pos / kPage), r = (int)(pos % kPage);
+    const float* src = T.pages + (size_t)page * T.dpad * kPage + r;
+    __half* img = reinterpret_cast<__half*>(tcpages + (size_t)page * tc_page_bytes(kp));
     const bool real = pos < T.n_points;
-    double n2 = 0.0;
+    double n2 = 0.0, rest = 0.0;
     for (int k = 0; k < kp; k++) {
-        float v = 0.f;
+        __half hv = __float2half_rn(0.f);
         if (k < T.dim) {
             if (real) {
-                float p = src[(size_t)k * kPage];
-                double c = (double)p - (double)mean[k];
+                double c = (double)src[(size_t)k * kPage] - (double)mean[k];
                 n2 += c * c;
-                v = to_tf32((float)c);
+                hv = __float2half_rn((float)(c * (double)scale));
             }
-        } else if (k == T.dim) {
-            v = real ? to_tf32((float)n2) : 1.0e30f;  // padded positions can never pass the filter
-        } else if (k == T.dim + 1) {
-            v = real ? to_tf32((float)(n2 - (double)to_tf32((float)n2))) : 0.f;
+        } else if (k < T.dim + 3) {
+            // s^2 |p'|^2 / u as hi + mid + lo (each FP16, together 33 bits); padded positions: a value no bound reaches
+            if (k == T.dim) rest = real ? n2 * (double)scale * (double)scale / (double)norm_unit : 60000.0;
+            hv = __float2half_rn((float)rest);
+            rest -= (double)__half2float(hv);
         }
-        dst[(((size_t)(k >> 2) * 32 + g) * 8 + r) * 4 + (k & 3)] = v;
+        img[(((size_t)(k >> 3) * 32 + (r >> 3)) * 8 + (r & 7)) * 8 + (k & 7)] = hv;
     }
 }
 
 // -------------------------------------------------------------------------------------------------------------
-// eligibility: the prefilter pays off when its error margin is small against the K-th distance after the seed scan
-// counters[6] += queries whose margin is below 1/16 of the seed K-th distance^2
+// per-query rounding margin of the filter (unscaled units):
+//   |S/s^2 + |q'|^2 - |p-q|^2| <= 2(2^-10+2^-21) B + 2^-19 (2B + Nmax) + subnormal term,   B >= sum_j |q'_j p'_j|
 // -------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float tc_margin(const float* qc_abs_sum_pmax, float qnorm, float pnorm_max) {
-    // |S_mma + |q'|^2 - |p-q|^2| <= 2(2^-10+2^-20) B + 2^-19 (2B + Nmax),  B >= sum_j |q'_j p'_j|  
-    float B = fminf(*qc_abs_sum_pmax, qnorm * pnorm_max);
-    return (2.0f * (9.765625e-4f + 9.5367432e-7f) * B + 1.9073486e-6f * (2.0f * B + pnorm_max * pnorm_max)) * 1.01f;
+__device__ __forceinline__ float tc_margin(float abs_sum_pmax, float qnorm, float q_l1, float pnorm_max, float pabs_sum, float scale) {
+    float B = fminf(abs_sum_pmax, qnorm * pnorm_max);
+    float m = 2.0f * (9.765625e-4f + 4.7683716e-7f) * B + 1.9073486e-6f * (2.0f * B + pnorm_max * pnorm_max);
+    m += 1.1920929e-7f * (q_l1 + pabs_sum) / scale;  // FP16 subnormals: absolute error 2^-25 per scaled operand
+    return m * 1.01f;
 }
 
+// eligibility: the prefilter pays off when its error margin is small against the K-th distance after the seed scan.
+// counters[6] += queries whose margin is below 1/16 of the seed K-th distance^2 (and which fit FP16's range)
 __global__ void k_tc_eligibility(DevTree T, const float* __restrict__ q, const int* __restrict__ q_order, int nq, int K,
                                  const uint64_t* __restrict__ state, const float* __restrict__ mean, const float* __restrict__ pmax,
-                                 float pnorm_max, unsigned long long* __restrict__ counters) {
+                                 float pnorm_max, float pabs_sum, float scale, unsigned long long* __restrict__ counters) {
     int slot = blockIdx.x * blockDim.x + threadIdx.x;
     bool ok = false;
     if (slot < nq) {
         int qid = q_order[slot];
-        float s1 = 0.f, n2 = 0.f;
+        float s1 = 0.f, n2 = 0.f, l1 = 0.f, amax = 0.f;
         for (int j = 0; j < T.dim; j++) {
             float c = q[(size_t)qid * T.dim + j] - mean[j];
             s1 = fmaf(fabsf(c), pmax[j], s1);
             n2 = fmaf(c, c, n2);
+            l1 += fabsf(c);
+            amax = fmaxf(amax, fabsf(c));
         }
-        s1 *= 1.0001f;
-        float margin = tc_margin(&s1, sqrtf(n2) * 1.0001f, pnorm_max);
+        float margin = tc_margin(s1 * 1.0001f, sqrtf(n2) * 1.0001f, l1 * 1.0001f, pnorm_max, pabs_sum, scale);
         float kth = __uint_as_float((uint32_t)(state[(size_t)slot * K + K - 1] >> 32));
-        ok = (kth < 3.0e38f) && (margin * 16.f <= kth);
+        ok = (kth < 3.0e38f) && (margin * 16.f <= kth) && (2.f * amax * scale < 60000.f);
     }
     unsigned m = __ballot_sync(0xffffffffu, ok);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[6], (unsigned long long)__popc(m));
@@ -177,29 +173,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     const int dpad = T.dpad, K = P.K, kp = TP.kp;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    float* stage_mem = reinterpret_cast<float*>(base);                              // [stages][kTcKSlice/4][32][8][4]
-    const int stage_k = min(kp, kTcKSlice);                                         // K elements held by one stage
-    float* sA = stage_mem + (size_t)kTcStages * stage_k * kPage;                    // [kp/4][16][8][4]
-    float* qs = sA + (size_t)kTcQ * kp;                                             // [dpad][128] original queries
-    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)dpad * kTcQ);        // [128][K]
-    uint64_t* queues = lists + (size_t)kTcQ * K;                                    // [16][kTcQueueCap]
-    int2* seed_rg = reinterpret_cast<int2*>(queues + (size_t)kTcEpiWarps * kTcQueueCap);  // [128]
-    int* a0s = reinterpret_cast<int*>(seed_rg + kTcQ);
+    const int stage_k = min(kp, kTcKSlice);                                    // K elements held by one stage
+    const uint32_t stage_bytes = (uint32_t)stage_k * 512;
+    unsigned char* stage_mem = base;                                           // [stages][stage_k/8][32][8][8] halves
+    __half* sA = reinterpret_cast<__half*>(stage_mem + (size_t)kTcStages * stage_bytes);  // [kp/8][16][8][8]
+    float* qs = reinterpret_cast<float*>(sA + (size_t)kTcQ * kp);              // [dpad][128] original queries
+    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)dpad * kTcQ);   // [128][K]
+    uint64_t* queues = lists + (size_t)kTcQ * K;                               // [16][kTcQueueCap]
+    int* a0s = reinterpret_cast<int*>(queues + (size_t)kTcEpiWarps * kTcQueueCap);
     int* a1s = a0s + kTcQ;
     int* qids = a1s + kTcQ;
     uint64_t* full_b = reinterpret_cast<uint64_t*>(qids + kTcQ);
     uint64_t* empty_b = full_b + kTcStages;
-    uint64_t* tfull_b = empty_b + kTcStages;   // [4]
-    uint64_t* tempty_b = tfull_b + 4;          // [4]
+    uint64_t* tfull_b = empty_b + kTcStages;      // [4]
+    uint64_t* tempty_b = tfull_b + 4;             // [4]
     int* qcount = reinterpret_cast<int*>(tempty_b + 4);  // [16]
     int* qlock = qcount + kTcEpiWarps;                   // [4] one lock per lane quadrant (four warps share its lists)
-    int* misc = qlock + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qlock + 4);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int q_begin = tile * kTcQ;
     const int nq_tile = min(kTcQ, P.nq - q_begin);
+    const float scale = TP.scale;
 
     // ---- set-up ---------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -231,21 +227,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
         a1s[i] = a1;
     }
     __syncthreads();
-    // queries: exact copy (dim-major) and the A operand: row q = (-2 tf32(q'_j) ..., 1, 1, 0 ...)
+    // queries: exact copy (dim-major) and the A operand: row q = fp16(-2 s q'_j); a query outside FP16's range gets a
+    // zero row (its bound is set to "everything passes" below, so it stays exact, only slow)
     for (int i = tid; i < kTcQ * dpad; i += blockDim.x) {
         int qi = i / dpad, j = i - qi * dpad;
         int qid = qids[qi];
         qs[j * kTcQ + qi] = (qid >= 0 && j < T.dim) ? P.q[(size_t)qid * T.dim + j] : 0.f;
     }
+    __syncthreads();
     for (int i = tid; i < kTcQ * kp; i += blockDim.x) {
         int qi = i / kp, k = i - qi * kp;
-        int qid = qids[qi];
         float v = 0.f;
-        if (qid >= 0) {
-            if (k < T.dim) v = -2.0f * to_tf32((float)((double)P.q[(size_t)qid * T.dim + k] - (double)TP.mean[k]));
-            else if (k <= T.dim + 1) v = 1.0f;
+        if (qids[qi] >= 0 && k < T.dim) {
+            bool in_range = true;
+            for (int j = 0; j < T.dim; j++) in_range &= fabsf(qs[j * kTcQ + qi] - TP.mean[j]) * 2.f * scale < 60000.f;
+            if (in_range) v = (float)(-2.0 * ((double)qs[k * kTcQ + qi] - (double)TP.mean[k]) * (double)scale);
+        } else if (k >= T.dim && k < T.dim + 3) {
+            v = TP.norm_unit;  // multiplies the norm slots of the point operand (every row, also padded ones)
         }
-        sA[(((size_t)(k >> 2) * (kTcQ / 8) + (qi >> 3)) * 8 + (qi & 7)) * 4 + (k & 3)] = v;
+        sA[(((size_t)(k >> 3) * (kTcQ / 8) + (qi >> 3)) * 8 + (qi & 7)) * 8 + (k & 7)] = __float2half_rn(v);
     }
     for (int i = tid; i < kTcQ * K; i += blockDim.x) {
         int qi = i / K;
@@ -259,104 +259,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
 
     // No seed-page exclusion here: the seed scan ran on 32-query tiles, so a page may have been seed-scanned for some of
     // these 128 queries only.  Re-scanning is cheap in this kernel and list insertion is idempotent.
-    PageWalk walk(P.ranges + (size_t)tile * kRangeCap, P.n_ranges + (size_t)tile * kMaxCuts, T.n_cuts, kJobRanges, seed_rg, 0);
+    PageWalk walk(P.ranges + (size_t)tile * kRangeCap, P.n_ranges + (size_t)tile * kMaxCuts, T.n_cuts, kJobRanges, nullptr, 0);
     const int n_slices = (kp + kTcKSlice - 1) / kTcKSlice;
     int page;
 
     if (warp == kTcEpiWarps) {
         // ================= producer =================
         if (lane == 0) {
-            uint32_t it = 0;
-            [[maybe_unused]] long long w_empty = 0, w_other = 0;
-            TCP_T0();
+            uint32_t it = 0, pg = 0;
+            const size_t page_bytes = tc_page_bytes(kp);
             while (walk.next(page)) {
+                const unsigned char* src = TP.tcpages + (size_t)page * page_bytes;
                 for (int s = 0; s < n_slices; s++, it++) {
-                    int st = it % kTcStages;
-                    uint32_t ph = (it / kTcStages) & 1;
-                    TCP_ADD(w_other);
-                    mbar_wait_backoff(&empty_b[st], ph ^ 1);
-                    TCP_ADD(w_empty);
-                    int kk = min(kTcKSlice, kp - s * kTcKSlice);
-                    uint32_t bytes = (uint32_t)kk * kPage * 4;
+                    const uint32_t st = it % kTcStages;
+                    const uint32_t ph = (it / kTcStages) & 1;
+                    mbar_wait(&empty_b[st], ph ^ 1);
+                    const uint32_t bytes = (uint32_t)min(kTcKSlice, kp - s * kTcKSlice) * 512;
                     mbar_arrive_expect_tx(&full_b[st], bytes);
-                    bulk_g2s(stage_mem + (size_t)st * stage_k * kPage, TP.tcpages + ((size_t)page * kp + (size_t)s * kTcKSlice) * kPage, bytes,
-                             &full_b[st]);
+                    bulk_g2s(stage_mem + (size_t)st * stage_bytes, src + (size_t)s * kTcKSlice * 512, bytes, &full_b[st]);
                 }
+                pg++;
             }
-#ifdef SCHT_TC_PROF
-            atomicAdd(&P.counters[8], (unsigned long long)w_empty);
-            atomicAdd(&P.counters[9], (unsigned long long)w_other);
-#endif
         }
     } else if (warp > kTcEpiWarps) {
         // ================= MMA issuers: warp 17+g issues the MMAs of half page g; the whole warp walks the pipeline,
         // one elected lane issues (keeps tcgen05 on the uniform datapath) =================
-        {
-            const int g = warp - (kTcEpiWarps + 1);
-            constexpr int kHalf = kPage / 2;  // N of one MMA: a half page
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kHalf >> 3) << 17) | ((uint32_t)(kTcQ >> 4) << 24);
-            // Descriptors are affine in (slice, k8, stage): two bases built once plus 16-byte-unit offsets.
-            constexpr uint32_t kAStep = 2 * (kTcQ / 8) * 128 / 16;   // two K chunks of the A image, in 16-byte units
-            constexpr uint32_t kBStep = 2 * (kPage / 8) * 128 / 16;  // two K chunks of a B stage
-            constexpr uint32_t kBHalf = (kHalf / 8) * 128 / 16;      // second half page inside a K chunk
-            const uint32_t kBStage = (uint32_t)stage_k * kPage * 4 / 16;
-            const uint64_t da0 = umma_desc_kmajor(smem_u32(sA), (kTcQ / 8) * 128, 128);
-            const uint64_t db0 = umma_desc_kmajor(smem_u32(stage_mem), (kPage / 8) * 128, 128) + (uint64_t)((uint32_t)g * kBHalf);
-            uint32_t it = 0, pg = 0;
-            [[maybe_unused]] long long m_full = 0, m_tempty = 0, m_issue = 0;
-            TCP_T0();
-            while (walk.next(page)) {
-                // half page g of page pg -> buffer 2*(pg&1)+g, used for the (pg>>1)-th time
-                const uint32_t buf = 2 * (pg & 1) + g;
-                const uint32_t d_tmem = tmem + buf * kHalf;
-                TCP_ADD(m_issue);
-#ifdef SCHT_TC_PROF
-                const bool tr = TP.trace && tile == 0 && g == 0 && lane == 0 && pg >= 2000 && pg < 2064;
-                if (tr) TP.trace[(pg - 2000) * 8 + 0] = clock64();
-#endif
-                mbar_wait(&tempty_b[buf], ((pg >> 1) & 1) ^ 1);
-#ifdef SCHT_TC_PROF
-                if (tr) TP.trace[(pg - 2000) * 8 + 1] = clock64();
-#endif
-                TCP_ADD(m_tempty);
-                for (int s = 0; s < n_slices; s++, it++) {
-                    const uint32_t st = it % kTcStages;
-                    const uint32_t ph = (it / kTcStages) & 1;
-                    TCP_ADD(m_issue);
-                    mbar_wait(&full_b[st], ph);
-#ifdef SCHT_TC_PROF
-                    if (tr) TP.trace[(pg - 2000) * 8 + 2] = clock64();
-#endif
-                    TCP_ADD(m_full);
-                    tc_fence_after();
-                    const int n8 = min(kTcKSlice, kp - s * kTcKSlice) / 8;
-                    const uint64_t da_s = da0 + (uint64_t)((uint32_t)s * (kTcKSlice / 8) * kAStep);
-                    const uint64_t db_s = db0 + (uint64_t)(st * kBStage);
-                    if (elect_one_sync()) {
-#pragma unroll 4
-                        for (int k8 = 0; k8 < n8; k8++)
-                            umma_tf32(d_tmem, da_s + (uint64_t)((uint32_t)k8 * kAStep), db_s + (uint64_t)((uint32_t)k8 * kBStep), idesc,
-                                      (s > 0 || k8 > 0) ? 1u : 0u);
-                        if (s == n_slices - 1) umma_commit(&tfull_b[buf]);
-                        umma_commit(&empty_b[st]);  // the stage may be refilled once both issuers' MMAs have read it
-                    }
-                    __syncwarp();
-#ifdef SCHT_TC_PROF
-                    if (tr) TP.trace[(pg - 2000) * 8 + 3] = clock64();
-#endif
+        const int g = warp - (kTcEpiWarps + 1);
+        constexpr int kHalf = kPage / 2;  // N of one MMA: a half page
+        // kind::f16: D = F32 (1<<4), A = B = F16 (format 0), K-major both, N>>3, M>>4
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(kHalf >> 3) << 17) | ((uint32_t)(kTcQ >> 4) << 24);
+        // Descriptors are affine in (slice, k16, stage): two bases built once plus 16-byte-unit offsets.
+        constexpr uint32_t kAStep = 2 * (kTcQ / 8) * 128 / 16;   // two K chunks (16 halves) of the A image, in 16-byte units
+        constexpr uint32_t kBStep = 2 * (kPage / 8) * 128 / 16;  // two K chunks of a B stage
+        constexpr uint32_t kBHalf = (kHalf / 8) * 128 / 16;      // second half page inside a K chunk
+        const uint32_t kBStage = stage_bytes / 16;
+        const uint64_t da0 = umma_desc_kmajor(smem_u32(sA), (kTcQ / 8) * 128, 128);
+        const uint64_t db0 = umma_desc_kmajor(smem_u32(stage_mem), (kPage / 8) * 128, 128) + (uint64_t)((uint32_t)g * kBHalf);
+        uint32_t it = 0, pg = 0;
+        while (walk.next(page)) {
+            // half page g of page pg -> buffer 2*(pg&1)+g, used for the (pg>>1)-th time
+            const uint32_t buf = 2 * (pg & 1) + g;
+            const uint32_t d_tmem = tmem + buf * kHalf;
+            mbar_wait(&tempty_b[buf], ((pg >> 1) & 1) ^ 1);
+            for (int s = 0; s < n_slices; s++, it++) {
+                const uint32_t st = it % kTcStages;
+                const uint32_t ph = (it / kTcStages) & 1;
+                mbar_wait(&full_b[st], ph);
+                tc_fence_after();
+                const int n16 = min(kTcKSlice, kp - s * kTcKSlice) / 16;
+                const uint64_t da_s = da0 + (uint64_t)((uint32_t)s * (kTcKSlice / 16) * kAStep);
+                const uint64_t db_s = db0 + (uint64_t)(st * kBStage);
+                if (elect_one_sync()) {
+#pragma unroll 2
+                    for (int k16 = 0; k16 < n16; k16++)
+                        umma_f16(d_tmem, da_s + (uint64_t)((uint32_t)k16 * kAStep), db_s + (uint64_t)((uint32_t)k16 * kBStep), idesc,
+                                 (s > 0 || k16 > 0) ? 1u : 0u);
+                    if (s == n_slices - 1) umma_commit(&tfull_b[buf]);
+                    umma_commit(&empty_b[st]);  // the stage may be refilled once both issuers' MMAs have read it
                 }
-                pg++;
+                __syncwarp();
             }
-#ifdef SCHT_TC_PROF
-            if (lane == 0 && g == 0) {
-                atomicAdd(&P.counters[10], (unsigned long long)m_full);
-                atomicAdd(&P.counters[11], (unsigned long long)m_tempty);
-                atomicAdd(&P.counters[12], (unsigned long long)m_issue);
-            }
-#endif
+            pg++;
         }
     } else {
-        // ================= epilogue: thread = query (TMEM lane), this warp's 128 columns of every page =================
+        // ================= epilogue: thread = query (TMEM lane) =================
         // quad = TMEM lane quadrant (= warp id % 4, a hardware rule), sub = which 64 columns of the buffer,
         // half = pipeline group = which half page of every page
         const int quad = warp & 3, sub = (warp >> 2) & 1, half = warp >> 3;
@@ -366,17 +332,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
         int* lock = &qlock[quad];
         const bool valid_q = qi < nq_tile;
         // per-query constants of the filter
-        float qn2 = 0.f, s1 = 0.f;
+        float qn2 = 0.f, s1 = 0.f, l1 = 0.f, amax = 0.f;
         for (int j = 0; j < T.dim; j++) {
             float c = (float)((double)qs[j * kTcQ + qi] - (double)TP.mean[j]);
             qn2 = fmaf(c, c, qn2);
             s1 = fmaf(fabsf(c), TP.pmax[j], s1);
+            l1 += fabsf(c);
+            amax = fmaxf(amax, fabsf(c));
         }
-        s1 *= 1.0001f;
-        const float margin = tc_margin(&s1, sqrtf(qn2) * 1.0001f, TP.pnorm_max) + qn2 * 1.0e-5f;  // + slack for qn2's own rounding
+        const bool in_range = 2.f * amax * scale < 60000.f;
+        const float margin = tc_margin(s1 * 1.0001f, sqrtf(qn2) * 1.0001f, l1 * 1.0001f, TP.pnorm_max, TP.pabs_sum, scale) + qn2 * 1.0e-5f;
+        const float s2 = scale * scale;
+        const float pad_bound = 40000.f * TP.norm_unit;  // real points stay below 32768 u + |G|, padded ones sit at 60000 u
         auto bound_of = [&](float kth) {
-            // S passes when S <= kth(1+2^-20) - |q'|^2 + margin ; padded query slots never pass
-            return valid_q ? fminf(kth * 1.000001f, 3.0e38f) - qn2 + margin : -3.0e38f;
+            // S passes when S <= s^2 (kth(1+2^-20) - |q'|^2 + margin); padded query slots never pass; a query outside
+            // FP16's range has a zero operand row and lets every real point pass (norms of padded positions are 3e38)
+            // (the norm slots of padded positions hold 60000 u, above every real s^2|p'|^2 and above pad_bound)
+            if (!valid_q) return -3.0e38f;
+            if (!in_range) return pad_bound;
+            return fminf((fminf(kth * 1.000001f, 3.0e38f) - qn2 + margin) * s2, pad_bound);
         };
         float Tq = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));
         unsigned long long n_pairs = 0;
@@ -433,10 +407,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
             __syncwarp();
         };
 
-        // Balanced min tree over 32 accumulator values (FMNMX3, depth 4).  Rare path (some lane has a value under its
-        // bound): each such lane builds the bit mask of its surviving columns, reserves that many queue slots with ONE
-        // shared-memory atomic and writes them; lanes without a hit only wait at the reconvergence point.
-        auto process = [&](const uint32_t (&v)[32], int col0) {
+        // 32 columns: balanced min tree (FMNMX3, depth 4).  Rare path (some lane has a value under its bound): each such
+        // lane builds the bit mask of its surviving columns, reserves that many queue slots with ONE shared-memory atomic
+        // and writes them; lanes without a hit only wait at the reconvergence point.
+        auto process = [&](uint32_t (&v)[32], int col0) {
             float m[11];
 #pragma unroll
             for (int i = 0; i < 10; i++) m[i] = fminf(fminf(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1])), __uint_as_float(v[3 * i + 2]));
@@ -486,25 +460,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
         };
 
         uint32_t pg = 0;
-        [[maybe_unused]] long long e_wait = 0, e_work = 0, e_drain = 0;
-        TCP_T0();
         while (walk.next(page)) {
             const uint32_t buf = 2 * (pg & 1) + half;
-            TCP_ADD(e_work);
-#ifdef SCHT_TC_PROF
-            const bool tr = TP.trace && tile == 0 && warp == 0 && lane == 0 && pg >= 2000 && pg < 2064;
-            if (tr) TP.trace[(pg - 2000) * 8 + 4] = clock64();
-#endif
             mbar_wait(&tfull_b[buf], (pg >> 1) & 1);
-#ifdef SCHT_TC_PROF
-            if (tr) TP.trace[(pg - 2000) * 8 + 5] = clock64();
-#endif
-            TCP_ADD(e_wait);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + buf * 128 + sub * 64;
             const int col0 = half * 128 + sub * 64;
-            // (four epilogue warps per scheduler hide the TMEM-load latency; one 32-column register buffer keeps the
-            // kernel inside the 96-register budget of a 608-thread CTA)
             uint32_t va[32];
             tmem_ld32(taddr, va);
             tmem_ld_wait();
@@ -515,30 +476,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_b[buf]);
-#ifdef SCHT_TC_PROF
-            if (tr) TP.trace[(pg - 2000) * 8 + 6] = clock64();
-#endif
             process(va, col0 + 32);
-#ifdef SCHT_TC_PROF
-            if (tr) TP.trace[(pg - 2000) * 8 + 7] = clock64();
-#endif
             if (half == 0 && sub == 0) n_pairs += (unsigned long long)min(kPage, T.n_points - page * kPage);
-            TCP_ADD(e_work);
             {
                 const int qn = *reinterpret_cast<volatile int*>(mycount);  // warp-uniform: only this warp changes it
                 if (qn >= 128) drain(qn);
             }
-            TCP_ADD(e_drain);
             pg++;
         }
         drain(*reinterpret_cast<volatile int*>(mycount));
-#ifdef SCHT_TC_PROF
-        if (lane == 0 && warp == 0) {
-            atomicAdd(&P.counters[13], (unsigned long long)e_wait);
-            atomicAdd(&P.counters[14], (unsigned long long)e_work);
-            atomicAdd(&P.counters[15], (unsigned long long)e_drain);
-        }
-#endif
         // all four warps of the quadrant must be done before the lists are final
         asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
 
