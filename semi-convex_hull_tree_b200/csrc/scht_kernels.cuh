@@ -331,30 +331,34 @@ struct PageWalk {
     int n_groups, stride;
     const int2* seed;
     int n_seed;  // 0: nothing to skip
-    int g, r, page, sr;
+    int g, r, cnt_g, page, cur_end, sr;  // pages [page, cur_end) of the current range are still to be returned
     __device__ PageWalk(const int2* l, const int* c, int ng, int st, const int2* s, int ns)
-        : list(l), cnt(c), n_groups(ng), stride(st), seed(s), n_seed(ns), g(0), r(0), page(0), sr(0) {}
-    __device__ bool next(int& out) {
+        : list(l), cnt(c), n_groups(ng), stride(st), seed(s), n_seed(ns), g(0), r(0), page(0), cur_end(0), sr(0) {
+        cnt_g = (ng > 0) ? c[0] : 0;
+    }
+    __device__ __forceinline__ bool next(int& out) {
         for (;;) {
-            if (g >= n_groups) return false;
-            if (r >= cnt[g]) {
+            if (page < cur_end) {  // fast path: registers only (the range list lives in global memory)
+                if (n_seed) {
+                    while (sr < n_seed && seed[sr].y <= page) sr++;
+                    if (sr < n_seed && page >= seed[sr].x) {
+                        page = seed[sr].y;
+                        continue;
+                    }
+                }
+                out = page++;
+                return true;
+            }
+            while (g < n_groups && r >= cnt_g) {
                 g++;
                 r = 0;
-                continue;
+                if (g < n_groups) cnt_g = cnt[g];
             }
+            if (g >= n_groups) return false;
             const int2 rg = list[(size_t)g * stride + r];
-            if (page < rg.x) page = rg.x;
-            if (page >= rg.y) {
-                r++;
-                continue;
-            }
-            while (sr < n_seed && seed[sr].y <= page) sr++;
-            if (sr < n_seed && page >= seed[sr].x) {
-                page = seed[sr].y;
-                continue;
-            }
-            out = page++;
-            return true;
+            r++;
+            if (rg.x > page) page = rg.x;
+            cur_end = rg.y;
         }
     }
 };

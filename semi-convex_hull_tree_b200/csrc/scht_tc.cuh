@@ -264,9 +264,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     int page;
 
     if (warp == kTcEpiWarps) {
-        // ================= producer =================
-        if (lane == 0) {
-            uint32_t it = 0, pg = 0;
+        // ================= producer: the whole warp walks, one elected lane issues the bulk copies =================
+        {
+            uint32_t it = 0;
             const size_t page_bytes = tc_page_bytes(kp);
             while (walk.next(page)) {
                 const unsigned char* src = TP.tcpages + (size_t)page * page_bytes;
@@ -275,10 +275,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                     const uint32_t ph = (it / kTcStages) & 1;
                     mbar_wait(&empty_b[st], ph ^ 1);
                     const uint32_t bytes = (uint32_t)min(kTcKSlice, kp - s * kTcKSlice) * 512;
-                    mbar_arrive_expect_tx(&full_b[st], bytes);
-                    bulk_g2s(stage_mem + (size_t)st * stage_bytes, src + (size_t)s * kTcKSlice * 512, bytes, &full_b[st]);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(&full_b[st], bytes);
+                        bulk_g2s(stage_mem + (size_t)st * stage_bytes, src + (size_t)s * kTcKSlice * 512, bytes, &full_b[st]);
+                    }
+                    __syncwarp();
                 }
-                pg++;
             }
         }
     } else if (warp > kTcEpiWarps) {
