@@ -33,6 +33,7 @@ WORKLOADS = {
     # name: (n, dim, nq, K, pct, kind)
     "uniform_1Mx16_q100k_K10": (1_000_000, 16, 100_000, 10, 0.0005, "uniform"),
     "gauss_10Mx32_q1M_K10": (10_000_000, 32, 1_000_000, 10, 0.00005, "gauss1000"),
+    "gauss_2Mx32_q200k_K10": (2_000_000, 32, 200_000, 10, 0.00025, "gauss1000"),
     "siftlike_1Mx128_q100k_K10": (1_000_000, 128, 100_000, 10, 0.0005, "sift"),
     "posture_like_78095x15_self_K10": (78_095, 15, 78_095, 10, 0.005, "posture"),
     "smoke_50kx16_q4k_K10": (50_000, 16, 4_096, 10, 0.005, "uniform"),
@@ -286,21 +287,38 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    tpeak = float(peaks.get("bf16_tflops", 1590.0))
     s_gpu = stats["dist_computations"] / max(1, stats["n_queries"])
     if s_ref is None:
         s_ref = s_gpu
-    alg_bytes = s_ref * dim * 4 * nq  # per step = per pair of leaf-scan launches (seed + main)
-    scan_s = stats["ms_scan"] / 1e3
-    achieved = alg_bytes / scan_s / 1e9
+    used_tc = stats["prefilter_batches"] > 0
+    # dominant kernel = the main leaf scan (k_scan_tc with the tensor-core prefilter, else k_scan); one launch per step
+    main_s = stats["ms_main_scan"] / 1e3
+    alg_bytes = s_ref * dim * 4 * nq  # points the REFERENCE algorithm scans x D x 4 B, for the queries of one step
+    achieved = alg_bytes / main_s / 1e9
     clk = (line["clocks"].get("sm_mhz") or 1965) * 1e6
+    pairs = stats["dist_computations"]
     line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
-                        "kernel": "k_scan (seed + main launch of one step)", "kernel_ms_per_step": stats["ms_scan"],
-                        "algorithmic_bytes_per_step": alg_bytes, "ref_scanned_points_per_query": s_ref, "gpu_scanned_points_per_query": s_gpu,
-                        "note": "pages are reused by every query of a tile from shared memory, so DRAM traffic is far below the algorithmic "
-                                "bytes and the binding unit is the FP32 pipe",
-                        "fp32_lane_ops_per_s": stats["dist_computations"] * dim * 2 / scan_s,
-                        "fp32_frac_of_128_lanes_per_clk_per_sm": stats["dist_computations"] * dim * 2 / scan_s / (148 * 128 * clk)}
+                        "kernel": "k_scan_tc (main scan, tensor-core prefilter + exact rescoring)" if used_tc else "k_scan (main scan)",
+                        "kernel_ms": stats["ms_main_scan"], "launches_per_step": 1,
+                        "algorithmic_bytes_per_launch": alg_bytes, "ref_scanned_points_per_query": s_ref, "gpu_scanned_points_per_query": s_gpu,
+                        "note": "algorithmic bytes per SURVEY 8d (reference-scanned points x D x 4 B). Every staged page is reused by all "
+                                "queries of a tile and re-read from L2 by the other tiles, so DRAM traffic is far below the algorithmic "
+                                "bytes and frac >> 1: the kernel is not HBM-bound (see `tensor` / `fp32` below and DESIGN.md 5)",
+                        "other_kernels_ms": {"seed_scan": stats["ms_seed_scan"], "traverse": stats["ms_traverse"],
+                                             "rest": stats["ms_device"] - stats["ms_seed_scan"] - stats["ms_traverse"] - stats["ms_main_scan"]}}
+    if used_tc:
+        kp = (dim + 3 + 15) // 16 * 16
+        line["roofline"]["tensor"] = {"achieved_tflops_algorithmic": pairs * dim * 2 / main_s / 1e12,
+                                      "achieved_tflops_issued": pairs * kp * 2 / main_s / 1e12, "peak_tflops": tpeak,
+                                      "frac_issued": pairs * kp * 2 / main_s / 1e12 / tpeak,
+                                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; FP16 and BF16 MMA run at the same rate)",
+                                      "note": "the MMA is 1/8 of the kernel time; the epilogue (one TMEM read + min per pair) and the "
+                                              "MMA->epilogue hand-off latency bound the kernel, not the tensor pipe"}
+    else:
+        line["roofline"]["fp32"] = {"lane_ops_per_s": pairs * dim * 2 / main_s,
+                                    "frac_of_128_lanes_per_clk_per_sm": pairs * dim * 2 / main_s / (148 * 128 * clk)}
     line["stats_one_step"] = stats
     print(json.dumps(line))
     if world > 1:

@@ -128,6 +128,9 @@ typedef struct scht_stats {
     int64_t kernel_launches;     /* number of kernels launched by the call */
     int64_t pages_listed;        /* (query,page) pairs the traversal kept for the main scan, x256 ~ candidate points */
     int64_t prefilter_batches;   /* batches whose main scan used the tensor-core prefilter */
+    double ms_seed_scan;         /* CUDA-event time of the seed scan (approximate leaves) */
+    double ms_traverse;          /* CUDA-event time of the eligibility + traversal/pruning kernels */
+    double ms_main_scan;         /* CUDA-event time of the main scan (k_scan or k_scan_tc) */
 } scht_stats;
 
 /* Uploads the tree to `device` (CUDA ordinal) in the device layout described in DESIGN.md. */

@@ -271,8 +271,9 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         TP.counters = ctr;
         // Sampled first: when the bounds keep >= 90 % of the pages for every 8th tile, they are not evaluated for the
         // other tiles (all their pages are listed); otherwise the remaining tiles are traversed too.
-        const int kSample = 8;
-        if (n_tiles_main >= 8 * kSample && h->traverse_sampling) {
+        // (about 24 sampled tiles, at least every 64th and at most every 8th tile)
+        const int kSample = std::max(8, std::min(64, n_tiles_main / 24));
+        if (n_tiles_main >= 64 && h->traverse_sampling) {
             unsigned long long before = 0, after = 0;
             TP.sel_mode = 1;
             TP.sel_step = kSample;
@@ -318,11 +319,28 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             TC.scale = h->tc_scale;
             TC.norm_unit = h->norm_unit;
             TC.kp = h->kp;
+#ifdef SCHT_TC_PROF
+            static long long* d_trace = nullptr;
+            if (!d_trace) cudaMalloc(&d_trace, 64 * 8 * 8);
+            cudaMemsetAsync(d_trace, 0, 64 * 8 * 8, s);
+            TC.trace = d_trace;
+#endif
             size_t smem = tc_smem_bytes(T.dpad, h->kp, K);
             CU_TRY(cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_scan_tc<<<n_tiles_main, kTcThreads, smem, s>>>(TC);
             CU_TRY(cudaGetLastError());
             h->tc_batches++;
+#ifdef SCHT_TC_PROF
+            {
+                long long tr[64 * 8];
+                cudaMemcpyAsync(tr, TC.trace, sizeof(tr), cudaMemcpyDeviceToHost, s);
+                cudaStreamSynchronize(s);
+                long long t0 = tr[2];
+                for (int i = 0; i < 40; i++)
+                    fprintf(stderr, "[trace pg %2d] prod: slot@%6lld sent@%6lld | mma: tempty@%6lld full@%6lld issued@%6lld | epi: tfull@%6lld released@%6lld done@%6lld\n", i,
+                            tr[i*8+0]-t0, tr[i*8+1]-t0, tr[i*8+2]-t0, tr[i*8+3]-t0, tr[i*8+4]-t0, tr[i*8+5]-t0, tr[i*8+6]-t0, tr[i*8+7]-t0);
+            }
+#endif
             used_tc = true;
         } else {
             rc = launch_scan(h, variant, P, s);
@@ -354,6 +372,11 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             CU_TRY(cudaEventElapsedTime(&c2, h->ev[3], h->ev[4]));
             st->ms_device += a;
             st->ms_scan += b + c2;
+            st->ms_seed_scan += brute ? 0.f : b;
+            st->ms_main_scan += brute ? b : c2;
+            float tr = 0;
+            CU_TRY(cudaEventElapsedTime(&tr, h->ev[2], h->ev[3]));
+            st->ms_traverse += tr;
         }
     }
     return SCHT_OK;
@@ -544,6 +567,19 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     TRY_H(upload(h, rc.data(), rc.size(), &T.node_rc));
     TRY_H(upload(h, t->leaf_start, (size_t)L, &T.leaf_start));
     TRY_H(upload(h, t->leaf_count, (size_t)L, &T.leaf_count));
+    {
+        // seed neighbourhood of every leaf: the smallest enclosing subtree with >= kSeedPoints points
+        std::vector<int> ss(L), se(L);
+        for (int i = 0; i < nn; i++) {
+            if (rec[i].leaf < 0) continue;
+            int a = i;
+            while (rec[a].pos1 - rec[a].pos0 < kSeedPoints && t->node_parent[a] >= 0) a = t->node_parent[a];
+            ss[rec[i].leaf] = rec[a].pos0;
+            se[rec[i].leaf] = rec[a].pos1;
+        }
+        TRY_H(upload(h, ss.data(), ss.size(), &T.seed_start));
+        TRY_H(upload(h, se.data(), se.size(), &T.seed_end));
+    }
     {
         std::vector<int32_t> oi((size_t)T.n_pages * kPage, -1);
         memcpy(oi.data(), t->sorted_to_orig, sizeof(int32_t) * (size_t)N);

@@ -30,6 +30,7 @@ constexpr int kRowsPerStage = 16;  // dims per shared-memory stage (16 rows x 25
 constexpr int kStages = 4;
 constexpr int kQPerWarp = 8;       // queries owned by one consumer warp
 constexpr int kMaxLevel = 32;      // constraints beyond this depth are ignored by the pruning bound (still valid)
+constexpr int kSeedPoints = 4096;  // size of the seed neighbourhood (positions) scanned before the traversal bounds are taken
 constexpr int kMaxCuts = 64;       // the traversal of one tile is split into <= 64 subtree jobs (one warp each)
 constexpr int kJobRanges = 8;      // page ranges per (tile, subtree job); overflow coalesces gaps (scans more, stays exact)
 constexpr int kRangeCap = kMaxCuts * kJobRanges;  // range slots per tile
@@ -57,6 +58,8 @@ struct DevTree {
     const float* node_rc;     // [n_nodes][dpad] right centre
     const int* leaf_start;    // [n_leaves]
     const int* leaf_count;    // [n_leaves]
+    const int* seed_start;    // [n_leaves] position range scanned first for a query whose approximate leaf this is: the
+    const int* seed_end;      // [n_leaves]   smallest enclosing subtree with >= kSeedPoints points (its own leaf at least)
     float xnorm_max;          // max ||x||_2 over the data set (pruning margin)
     int n_cuts, cut_depth;    // subtree roots the traversal is split at (pre-order), all at depth <= cut_depth
     const int* cut_path;      // [n_cuts][cut_depth+1] root-side path of each cut node (node ids, -1 padded), cut node last
@@ -273,7 +276,7 @@ __host__ __device__ inline size_t scan_smem_bytes(int n_cwarps, int dpad, int K)
     size_t b = (size_t)kStages * kRowsPerStage * kPage * 4;  // stages
     b += (size_t)dpad * tq * 4;                              // queries, dim-major
     b += tq * (size_t)K * 8;                                 // lists
-    b += tq * 8 + tq * 3 * 4 + 16;                           // seed ranges, a0, a1, qid, misc
+    b += tq * 8 + tq * 5 * 4 + 16;                           // seed ranges, a0, a1, s0, s1, qid, misc
     b += 2 * kStages * 8 + 64;                               // barriers
     return b;
 }
@@ -305,7 +308,7 @@ __device__ __forceinline__ int list_insert(uint64_t* L, int K, uint64_t key, int
     return 1;
 }
 
-// Ascending, merged page ranges covering the approximate leaves of a tile's (leaf-sorted) queries.
+// Ascending, merged page ranges covering the seed neighbourhoods of a tile's (leaf-sorted) queries.
 __device__ inline int build_seed_ranges(const int* a0s, const int* a1s, int nq_tile, int pos_lo, int pos_hi, int2* out) {
     int n = 0;
     for (int i = 0; i < nq_tile; i++) {
@@ -314,7 +317,7 @@ __device__ inline int build_seed_ranges(const int* a0s, const int* a1s, int nq_t
         int pb = a0 / kPage, pe = (a1 + kPage - 1) / kPage;
         if (n > 0 && pb <= out[n - 1].y) {
             out[n - 1].y = max(out[n - 1].y, pe);
-            if (pb < out[n - 1].x) out[n - 1].x = pb;  // cannot happen for leaf-sorted queries; keeps the list valid
+            if (pb < out[n - 1].x) out[n - 1].x = pb;  // (neighbourhoods of leaf-sorted queries are nested or ascending)
         } else {
             out[n++] = make_int2(pb, pe);
         }
@@ -376,7 +379,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
     int2* seed_rg = reinterpret_cast<int2*>(lists + (size_t)TQ * K);  // [TQ]
     int* a0s = reinterpret_cast<int*>(seed_rg + TQ);
     int* a1s = a0s + TQ;
-    int* qids = a1s + TQ;
+    int* s0s = a1s + TQ;   // seed neighbourhood of each query (a superset of its approximate leaf)
+    int* s1s = s0s + TQ;
+    int* qids = s1s + TQ;
     int* misc = qids + TQ;  // [0] number of seed ranges
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc + 4);
     uint64_t* empty_bar = full_bar + kStages;
@@ -397,14 +402,18 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
     for (int i = tid; i < TQ; i += blockDim.x) {
         int qid = (i < nq_tile) ? P.q_order[q_begin + i] : -1;
         qids[i] = qid;
-        int a0 = 0, a1 = 0;
+        int a0 = 0, a1 = 0, s0 = 0, s1 = 0;
         if (qid >= 0 && P.mode != kScanAll) {
             int leaf = P.q_leaf[qid];
             a0 = T.leaf_start[leaf];
             a1 = a0 + T.leaf_count[leaf];
+            s0 = T.seed_start[leaf];
+            s1 = T.seed_end[leaf];
         }
         a0s[i] = a0;
         a1s[i] = a1;
+        s0s[i] = s0;
+        s1s[i] = s1;
     }
     __syncthreads();
     for (int i = tid; i < TQ * dpad; i += blockDim.x) {
@@ -421,7 +430,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
     } else {
         for (int i = tid; i < TQ * K; i += blockDim.x) lists[i] = kEmptyKey;
     }
-    if (tid == 0) misc[0] = (P.mode == kScanAll) ? 0 : build_seed_ranges(a0s, a1s, nq_tile, P.pos_lo, P.pos_hi, seed_rg);
+    if (tid == 0) misc[0] = (P.mode == kScanAll) ? 0 : build_seed_ranges(s0s, s1s, nq_tile, P.pos_lo, P.pos_hi, seed_rg);
     __syncthreads();
 
     // ---- the page list of this tile (identical walk in the producer and in every consumer warp) ------------

@@ -14,11 +14,14 @@
 // the ~10^11 pairs are worth an exact evaluation (about 3 in 10^4).
 //
 // Roles: warps 0-15 epilogue, warp 16 = producer lane (cp.async.bulk of page slices already stored in the UMMA
-// K-major no-swizzle layout), warps 17/18 = MMA issuers.  The unit of the MMA->epilogue pipeline is a HALF page (128
-// points, N=128): the 512 TMEM columns hold four 128-column accumulator buffers.  Group g (MMA warp 17+g and epilogue
-// warps 8g..8g+7) owns half page g of every page and the buffers g and g+2, so two double-buffered chains run
-// interleaved and hide each other's hand-off latencies.  Epilogue warp w reads TMEM lanes 32(w%4)..+31 (thread =
-// query) and 64 of the 128 columns of its group's buffer.
+// K-major no-swizzle layout), warps 17-20 = MMA issuers, one per TMEM buffer.  The unit of the MMA->epilogue pipeline
+// is a HALF page (128 points, N=128): the 512 TMEM columns hold four 128-column accumulator buffers; half page g of
+// page p lives in buffer 2(p&1)+g.  Epilogue warps 8g..8g+7 process the half pages g: warp w reads TMEM lanes
+// 32(w%4)..+31 (thread = query) and 64 of the buffer's 128 columns; survivors go into the warp's ring.  Four
+// independent issue streams and two double-buffered epilogue groups hide the hand-off latencies (mbarrier waits, MMA
+// issue, commits: ~900 cycles per page for a single issuer).  Warps 21-24 are the RESCORERS: rescorer r consumes the rings of the four epilogue warps of lane quadrant r, re-evaluates the survivors
+// exactly, owns the quadrant's 32 top-K lists (no locks) and publishes the tightened bounds, so the MMA->epilogue
+// pipeline never waits for an exact evaluation.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -26,12 +29,18 @@
 
 namespace scht {
 
+#ifdef SCHT_TC_PROF
+#define TC_STAMP(cond, pg, slot) do { if ((cond) && tile == 0 && lane == 0 && (pg) >= 2000 && (pg) < 2064) TP.trace[((pg) - 2000) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TC_STAMP(cond, pg, slot)
+#endif
+
 constexpr int kTcQ = 128;          // queries per tile (MMA M)
 constexpr int kTcKSlice = 32;      // K elements (FP16) per shared-memory stage: 16 KB
 constexpr int kTcStages = 6;       // slice stages
 constexpr int kTcEpiWarps = 16;
-constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;
-constexpr int kTcQueueCap = 384;   // candidate queue entries per epilogue warp
+constexpr int kTcThreads = (kTcEpiWarps + 1 + 4 + 4) * 32;  // + producer, 4 MMA issuers, 4 rescorers
+constexpr int kTcQueueCap = 256;   // ring entries per epilogue warp (power of two)
 
 struct TcScanParams {
     ScanParams S;            // q, q_order, q_leaf, nq, K, write_mode, pos range, ranges (tile = 128 queries), state, outputs
@@ -43,6 +52,7 @@ struct TcScanParams {
     float scale;             // s (power of two)
     float norm_unit;         // power of two u: the norm slots hold s^2|p'|^2 / u, the query operand holds u
     int kp;                  // padded K (multiple of 16) = ceil16(dim + 3)
+    long long* trace;        // SCHT_TC_PROF builds: [64 pages][8] clock64 stamps of tile 0 (pages 2000..2063)
 };
 
 __host__ __device__ inline size_t tc_page_bytes(int kp) { return (size_t)kp * 512; }
@@ -51,11 +61,10 @@ __host__ __device__ inline size_t tc_smem_bytes(int dpad, int kp, int K) {
     size_t b = 1024;                                                         // alignment slack
     b += (size_t)kTcStages * (kp < kTcKSlice ? kp : kTcKSlice) * 512;        // B slice stages (<= 16 KB each)
     b += (size_t)kTcQ * kp * 2;                                              // A operand
-    b += (size_t)dpad * kTcQ * 4;                                            // original queries, dim-major (exact path)
     b += (size_t)kTcQ * K * 8;                                               // lists
     b += (size_t)kTcEpiWarps * kTcQueueCap * 8;                              // candidate queues
     b += (size_t)kTcQ * 3 * 4;                                               // a0, a1, qid
-    b += 512;                                                                // barriers, counters, tmem base
+    b += 1536;                                                               // barriers, ring counters, bounds, tmem base
     return b;
 }
 
@@ -177,8 +186,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     const uint32_t stage_bytes = (uint32_t)stage_k * 512;
     unsigned char* stage_mem = base;                                           // [stages][stage_k/8][32][8][8] halves
     __half* sA = reinterpret_cast<__half*>(stage_mem + (size_t)kTcStages * stage_bytes);  // [kp/8][16][8][8]
-    float* qs = reinterpret_cast<float*>(sA + (size_t)kTcQ * kp);              // [dpad][128] original queries
-    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)dpad * kTcQ);   // [128][K]
+    uint64_t* lists = reinterpret_cast<uint64_t*>(sA + (size_t)kTcQ * kp);     // [128][K]
     uint64_t* queues = lists + (size_t)kTcQ * K;                               // [16][kTcQueueCap]
     int* a0s = reinterpret_cast<int*>(queues + (size_t)kTcEpiWarps * kTcQueueCap);
     int* a1s = a0s + kTcQ;
@@ -187,9 +195,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     uint64_t* empty_b = full_b + kTcStages;
     uint64_t* tfull_b = empty_b + kTcStages;      // [4]
     uint64_t* tempty_b = tfull_b + 4;             // [4]
-    int* qcount = reinterpret_cast<int*>(tempty_b + 4);  // [16]
-    int* qlock = qcount + kTcEpiWarps;                   // [4] one lock per lane quadrant (four warps share its lists)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qlock + 4);
+    int* q_tail = reinterpret_cast<int*>(tempty_b + 4);  // [16] entries pushed (written by the epilogue warp)
+    int* q_head = q_tail + kTcEpiWarps;                  // [16] entries consumed (written by the rescorer)
+    int* q_done = q_head + kTcEpiWarps;                  // [16] the epilogue warp has finished
+    int* q_resv = q_done + kTcEpiWarps;                  // [16] ring slots reserved by the epilogue warp's lanes (>= tail)
+    float* tq_s = reinterpret_cast<float*>(q_resv + kTcEpiWarps);  // [128] current filter bound of every query
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tq_s + kTcQ);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -213,7 +224,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (tid < kTcEpiWarps + 4) qcount[tid] = 0;  // queue counters and quadrant locks
+    if (tid < 4 * kTcEpiWarps) q_tail[tid] = 0;  // ring counters, done flags, reservations (contiguous)
     for (int i = tid; i < kTcQ; i += blockDim.x) {
         int qid = (i < nq_tile) ? P.q_order[q_begin + i] : -1;
         qids[i] = qid;
@@ -229,19 +240,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     __syncthreads();
     // queries: exact copy (dim-major) and the A operand: row q = fp16(-2 s q'_j); a query outside FP16's range gets a
     // zero row (its bound is set to "everything passes" below, so it stays exact, only slow)
-    for (int i = tid; i < kTcQ * dpad; i += blockDim.x) {
-        int qi = i / dpad, j = i - qi * dpad;
-        int qid = qids[qi];
-        qs[j * kTcQ + qi] = (qid >= 0 && j < T.dim) ? P.q[(size_t)qid * T.dim + j] : 0.f;
-    }
-    __syncthreads();
     for (int i = tid; i < kTcQ * kp; i += blockDim.x) {
         int qi = i / kp, k = i - qi * kp;
         float v = 0.f;
         if (qids[qi] >= 0 && k < T.dim) {
+            const float* qrow = P.q + (size_t)qids[qi] * T.dim;
             bool in_range = true;
-            for (int j = 0; j < T.dim; j++) in_range &= fabsf(qs[j * kTcQ + qi] - TP.mean[j]) * 2.f * scale < 60000.f;
-            if (in_range) v = (float)(-2.0 * ((double)qs[k * kTcQ + qi] - (double)TP.mean[k]) * (double)scale);
+            for (int j = 0; j < T.dim; j++) in_range &= fabsf(qrow[j] - TP.mean[j]) * 2.f * scale < 60000.f;
+            if (in_range) v = (float)(-2.0 * ((double)qrow[k] - (double)TP.mean[k]) * (double)scale);
         } else if (k >= T.dim && k < T.dim + 3) {
             v = TP.norm_unit;  // multiplies the norm slots of the point operand (every row, also padded ones)
         }
@@ -251,6 +257,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
         int qi = i / K;
         lists[i] = (qi < nq_tile) ? P.state[(size_t)(q_begin + qi) * K + (i - qi * K)] : kEmptyKey;
     }
+    for (int i = tid; i < kTcQ; i += blockDim.x) tq_s[i] = -3.0e38f;  // real bounds are published below, before the pipeline starts
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // sA was written through the generic proxy
     tc_fence_before();
     __syncthreads();
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     if (warp == kTcEpiWarps) {
         // ================= producer: the whole warp walks, one elected lane issues the bulk copies =================
         {
-            uint32_t it = 0;
+            uint32_t it = 0, ppg = 0;
             const size_t page_bytes = tc_page_bytes(kp);
             while (walk.next(page)) {
                 const unsigned char* src = TP.tcpages + (size_t)page * page_bytes;
@@ -274,6 +281,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                     const uint32_t st = it % kTcStages;
                     const uint32_t ph = (it / kTcStages) & 1;
                     mbar_wait(&empty_b[st], ph ^ 1);
+                    TC_STAMP(s == 0, ppg, 0);
                     const uint32_t bytes = (uint32_t)min(kTcKSlice, kp - s * kTcKSlice) * 512;
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&full_b[st], bytes);
@@ -281,12 +289,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                     }
                     __syncwarp();
                 }
+                TC_STAMP(true, ppg, 1);
+                ppg++;
             }
         }
-    } else if (warp > kTcEpiWarps) {
+    } else if (warp > kTcEpiWarps && warp <= kTcEpiWarps + 4) {
         // ================= MMA issuers: warp 17+g issues the MMAs of half page g; the whole warp walks the pipeline,
         // one elected lane issues (keeps tcgen05 on the uniform datapath) =================
-        const int g = warp - (kTcEpiWarps + 1);
+        // one issuer per TMEM buffer: warp 17+m issues half page g = m&1 of the pages with parity m>>1 (buffer 2*(m>>1)+g);
+        // the hand-off latencies of consecutive pages (mbarrier waits, MMA issue, commits) then overlap
+        const int g = (warp - (kTcEpiWarps + 1)) & 1, my_par = (warp - (kTcEpiWarps + 1)) >> 1;
         constexpr int kHalf = kPage / 2;  // N of one MMA: a half page
         // kind::f16: D = F32 (1<<4), A = B = F16 (format 0), K-major both, N>>3, M>>4
         const uint32_t idesc = (1u << 4) | ((uint32_t)(kHalf >> 3) << 17) | ((uint32_t)(kTcQ >> 4) << 24);
@@ -299,14 +311,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
         const uint64_t db0 = umma_desc_kmajor(smem_u32(stage_mem), (kPage / 8) * 128, 128) + (uint64_t)((uint32_t)g * kBHalf);
         uint32_t it = 0, pg = 0;
         while (walk.next(page)) {
+            if ((int)(pg & 1) != my_par) {  // the other parity's issuer handles this page
+                it += n_slices;
+                pg++;
+                continue;
+            }
             // half page g of page pg -> buffer 2*(pg&1)+g, used for the (pg>>1)-th time
             const uint32_t buf = 2 * (pg & 1) + g;
             const uint32_t d_tmem = tmem + buf * kHalf;
             mbar_wait(&tempty_b[buf], ((pg >> 1) & 1) ^ 1);
+            TC_STAMP(g == 0, pg, 2);
             for (int s = 0; s < n_slices; s++, it++) {
                 const uint32_t st = it % kTcStages;
                 const uint32_t ph = (it / kTcStages) & 1;
                 mbar_wait(&full_b[st], ph);
+                TC_STAMP(g == 0 && s == 0, pg, 3);
                 tc_fence_after();
                 const int n16 = min(kTcKSlice, kp - s * kTcKSlice) / 16;
                 const uint64_t da_s = da0 + (uint64_t)((uint32_t)s * (kTcKSlice / 16) * kAStep);
@@ -317,26 +336,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                         umma_f16(d_tmem, da_s + (uint64_t)((uint32_t)k16 * kAStep), db_s + (uint64_t)((uint32_t)k16 * kBStep), idesc,
                                  (s > 0 || k16 > 0) ? 1u : 0u);
                     if (s == n_slices - 1) umma_commit(&tfull_b[buf]);
-                    umma_commit(&empty_b[st]);  // the stage may be refilled once both issuers' MMAs have read it
+                    umma_commit(&empty_b[st]);  // the stage may be refilled once both half pages' MMAs have read it
                 }
                 __syncwarp();
             }
+            TC_STAMP(g == 0, pg, 4);
             pg++;
         }
     } else {
-        // ================= epilogue: thread = query (TMEM lane) =================
-        // quad = TMEM lane quadrant (= warp id % 4, a hardware rule), sub = which 64 columns of the buffer,
-        // half = pipeline group = which half page of every page
-        const int quad = warp & 3, sub = (warp >> 2) & 1, half = warp >> 3;
+        // epilogue warps and rescorers share the per-query filter constants: thread = query of the lane quadrant
+        const bool is_epi = warp < kTcEpiWarps;
+        const int quad = is_epi ? (warp & 3) : (warp - (kTcEpiWarps + 5));
         const int qi = quad * 32 + lane;  // tile-local query
-        uint64_t* myq = queues + (size_t)warp * kTcQueueCap;
-        int* mycount = &qcount[warp];
-        int* lock = &qlock[quad];
         const bool valid_q = qi < nq_tile;
-        // per-query constants of the filter
         float qn2 = 0.f, s1 = 0.f, l1 = 0.f, amax = 0.f;
+        const float* my_qrow = P.q + (size_t)(valid_q ? qids[qi] : 0) * T.dim;
         for (int j = 0; j < T.dim; j++) {
-            float c = (float)((double)qs[j * kTcQ + qi] - (double)TP.mean[j]);
+            float c = valid_q ? (float)((double)my_qrow[j] - (double)TP.mean[j]) : 0.f;
             qn2 = fmaf(c, c, qn2);
             s1 = fmaf(fabsf(c), TP.pmax[j], s1);
             l1 += fabsf(c);
@@ -348,44 +364,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
         const float pad_bound = 40000.f * TP.norm_unit;  // real points stay below 32768 u + |G|, padded ones sit at 60000 u
         auto bound_of = [&](float kth) {
             // S passes when S <= s^2 (kth(1+2^-20) - |q'|^2 + margin); padded query slots never pass; a query outside
-            // FP16's range has a zero operand row and lets every real point pass (norms of padded positions are 3e38)
+            // FP16's range has a zero operand row and lets every real point pass
             // (the norm slots of padded positions hold 60000 u, above every real s^2|p'|^2 and above pad_bound)
             if (!valid_q) return -3.0e38f;
             if (!in_range) return pad_bound;
             return fminf((fminf(kth * 1.000001f, 3.0e38f) - qn2 + margin) * s2, pad_bound);
         };
-        float Tq = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));
-        unsigned long long n_pairs = 0;
-        unsigned int n_exact = 0, n_ins = 0;
 
-        // Exact re-evaluation of the queued candidates (reference arithmetic, 32 at a time) and insertion into the lists.
-        // The four warps of a lane quadrant share the 32 lists, so the insert phase runs under the quadrant's lock.
-        auto drain = [&](int n) {
-            __syncwarp();
-            for (int b0 = 0; b0 < n; b0 += 32) {
-                bool cand = false;
-                float d2 = 0.f;
-                int pos = 0, cq = 0;
-                if (b0 + lane < n) {
-                    uint64_t e = myq[b0 + lane];
-                    pos = (int)(uint32_t)e;
-                    cq = (int)(e >> 32);
-                    const int pgi = pos / kPage;
-                    const float* pg = T.pages + (size_t)pgi * dpad * kPage + (pos - pgi * kPage);
-                    const float* qq = qs + quad * 32 + cq;
-                    for (int j = 0; j < T.dim; j++) d2 = ref_acc_sq(d2, pg[(size_t)j * kPage] - qq[j * kTcQ]);
-                    n_exact++;
-                    cand = (d2 < 3.402823466e+38f) && (pos >= P.pos_lo) && (pos < P.pos_hi);
-                    // cheap pre-check against the (possibly stale) list tail, before taking the lock
-                    if (cand) cand = ((uint64_t)__float_as_uint(d2) << 32) <= lists[(size_t)(quad * 32 + cq) * K + K - 1];
-                }
-                unsigned m = __ballot_sync(0xffffffffu, cand);
-                if (m) {
-                    if (lane == 0) {
-                        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(50);
+        if (!is_epi) {
+            // ================= rescorer of lane quadrant `quad` =================
+            // Consumes the rings of the quadrant's four epilogue warps (single producer / single consumer each), re-evaluates
+            // the survivors with the reference arithmetic, inserts into the quadrant's lists (it is their only writer) and
+            // publishes every query's tightened bound in tq_s.
+            volatile int* v_tail = q_tail;
+            volatile int* v_head = q_head;
+            volatile int* v_done = q_done;
+            volatile float* v_tq = tq_s;
+            unsigned int n_exact = 0, n_ins = 0;
+            int heads[4] = {0, 0, 0, 0};
+            v_tq[qi] = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));  // bounds from the seed scan
+            __threadfence_block();
+            asm volatile("bar.sync %0, 160;" ::"r"(1 + quad) : "memory");  // ... visible to the quadrant's 4 epilogue warps
+            for (;;) {
+                bool all_done = true, did_work = false;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int w = quad + 4 * i;  // epilogue warp ids of this quadrant: quad, quad+4, quad+8, quad+12
+                    const int done = v_done[w];
+                    const int tail = v_tail[w];
+                    const int avail = tail - heads[i];
+                    all_done &= (done != 0) && (avail == 0);
+                    if (avail == 0) continue;
+                    did_work = true;
+                    __threadfence_block();  // entries below `tail` were written before it was published
+                    const int n = min(avail, 32);
+                    const uint64_t* ring = queues + (size_t)w * kTcQueueCap;
+                    bool cand = false;
+                    float d2 = 0.f;
+                    int pos = 0, cq = 0;
+                    if (lane < n) {
+                        const uint64_t e = ring[(heads[i] + lane) & (kTcQueueCap - 1)];
+                        pos = (int)(uint32_t)e;
+                        cq = (int)(e >> 32);
+                        const int pgi = pos / kPage;
+                        const float* pg = T.pages + (size_t)pgi * dpad * kPage + (pos - pgi * kPage);
+                        const float* qq = P.q + (size_t)qids[quad * 32 + cq] * T.dim;  // the query's original coordinates
+                        // loads first (8 dims at a time), then the sequential reference chain
+                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                            float pv[8], qv[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const bool in = j0 + u < T.dim;
+                                pv[u] = in ? pg[(size_t)(j0 + u) * kPage] : 0.f;
+                                qv[u] = in ? qq[j0 + u] : 0.f;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qv[u]);
+                        }
+                        n_exact++;
+                        cand = (d2 < 3.402823466e+38f) && (pos >= P.pos_lo) && (pos < P.pos_hi);
+                        if (cand) cand = ((uint64_t)__float_as_uint(d2) << 32) <= lists[(size_t)(quad * 32 + cq) * K + K - 1];
                     }
                     __syncwarp();
-                    __threadfence_block();
+                    heads[i] += n;
+                    if (lane == 0) v_head[w] = heads[i];  // the ring slots may be reused (values are in registers now)
+                    unsigned m = __ballot_sync(0xffffffffu, cand);
                     while (m) {
                         int src = __ffs(m) - 1;
                         m &= m - 1;
@@ -395,103 +439,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                         const int a0 = a0s[quad * 32 + ccq], a1 = a1s[quad * 32 + ccq];
                         uint32_t low = ((cpos >= a0 && cpos < a1) ? 0u : 0x80000000u) | (uint32_t)cpos;
                         uint64_t key = ((uint64_t)__float_as_uint(cd2) << 32) | low;
-                        volatile uint64_t* L = lists + (size_t)(quad * 32 + ccq) * K;
-                        if (key < L[K - 1]) n_ins += list_insert(const_cast<uint64_t*>(L), K, key, lane);
+                        uint64_t* L = lists + (size_t)(quad * 32 + ccq) * K;
+                        if (key < L[K - 1]) n_ins += list_insert(L, K, key, lane);
                     }
-                    __threadfence_block();
-                    __syncwarp();
-                    if (lane == 0) atomicExch(lock, 0);
+                    // publish the (possibly) tightened bound of this lane's query
+                    v_tq[qi] = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));
                 }
+                if (all_done) break;
+                if (!did_work) __nanosleep(100);
             }
             __syncwarp();
-            if (lane == 0) *mycount = 0;
-            Tq = bound_of(__uint_as_float((uint32_t)(reinterpret_cast<volatile uint64_t*>(lists)[(size_t)qi * K + K - 1] >> 32)));
-            __syncwarp();
-        };
-
-        // 32 columns: balanced min tree (FMNMX3, depth 4).  Rare path (some lane has a value under its bound): each such
-        // lane builds the bit mask of its surviving columns, reserves that many queue slots with ONE shared-memory atomic
-        // and writes them; lanes without a hit only wait at the reconvergence point.
-        auto process = [&](uint32_t (&v)[32], int col0) {
-            float m[11];
-#pragma unroll
-            for (int i = 0; i < 10; i++) m[i] = fminf(fminf(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1])), __uint_as_float(v[3 * i + 2]));
-            m[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-            float n0 = fminf(fminf(m[0], m[1]), m[2]), n1 = fminf(fminf(m[3], m[4]), m[5]), n2 = fminf(fminf(m[6], m[7]), m[8]),
-                  n3 = fminf(m[9], m[10]);
-            const float mn = fminf(fminf(fminf(n0, n1), n2), n3);
-            const bool hit = mn <= Tq;
-            if (__any_sync(0xffffffffu, hit)) {
-                uint32_t mask = 0;
-                if (hit) {
-#pragma unroll
-                    for (int c = 0; c < 32; c++) mask |= (__uint_as_float(v[c]) <= Tq ? 1u : 0u) << c;
-                }
-                for (;;) {
-                    bool fits = true;
-                    int slot = 0;
-                    const int cnt = __popc(mask);
-                    if (cnt) {
-                        slot = atomicAdd(mycount, cnt);
-                        fits = slot + cnt <= kTcQueueCap;
-                        if (fits) {
-                            while (mask) {
-                                const int c = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                myq[slot++] = ((uint64_t)(uint32_t)lane << 32) | (uint32_t)(page * kPage + col0 + c);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (!__any_sync(0xffffffffu, !fits)) break;
-                    // queue overflow (only while bounds are still loose): reservations are made in slot order, so the
-                    // entries below the first failed reservation are complete; drain them, then the failed lanes retry
-                    int first_bad = fits ? 0x7fffffff : slot;
-                    for (int o = 16; o; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
-                    drain(first_bad);
-                    if (fits) mask = 0;
-                    if (mask) {
-                        // the bound may have tightened: drop survivors that no longer pass
-                        uint32_t keep = 0;
-#pragma unroll
-                        for (int c = 0; c < 32; c++) keep |= (__uint_as_float(v[c]) <= Tq ? 1u : 0u) << c;
-                        mask &= keep;
-                    }
-                }
-            }
-        };
-
-        uint32_t pg = 0;
-        while (walk.next(page)) {
-            const uint32_t buf = 2 * (pg & 1) + half;
-            mbar_wait(&tfull_b[buf], (pg >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + buf * 128 + sub * 64;
-            const int col0 = half * 128 + sub * 64;
-            uint32_t va[32];
-            tmem_ld32(taddr, va);
-            tmem_ld_wait();
-            process(va, col0);
-            tmem_ld32(taddr + 32, va);
-            tmem_ld_wait();
-            // all of this warp's TMEM reads of the buffer are complete: hand it back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_b[buf]);
-            process(va, col0 + 32);
-            if (half == 0 && sub == 0) n_pairs += (unsigned long long)min(kPage, T.n_points - page * kPage);
-            {
-                const int qn = *reinterpret_cast<volatile int*>(mycount);  // warp-uniform: only this warp changes it
-                if (qn >= 128) drain(qn);
-            }
-            pg++;
-        }
-        drain(*reinterpret_cast<volatile int*>(mycount));
-        // all four warps of the quadrant must be done before the lists are final
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
-
-        // ---- results: the first warp of each quadrant writes its 32 queries ----
-        if (half == 0 && sub == 0) {
+            // ---- results: the rescorer owns the lists of its 32 queries ----
             for (int qq = 0; qq < 32; qq++) {
                 const int ql = quad * 32 + qq;
                 if (ql >= nq_tile) break;
@@ -516,14 +474,109 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                     for (int k = lane; k < K; k += 32) P.keys_out[(size_t)qid * K + k] = L[k];
                 }
             }
-        }
-        if (P.counters) {
-            int nvalid = max(0, min(32, nq_tile - quad * 32));
-            for (int o = 16; o; o >>= 1) n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
-            if (lane == 0) {
+            if (P.counters) {
+                for (int o = 16; o; o >>= 1) n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+                if (lane == 0) {
+                    atomicAdd(&P.counters[1], (unsigned long long)n_exact);
+                    atomicAdd(&P.counters[2], (unsigned long long)n_ins);
+                }
+            }
+        } else {
+            // ================= epilogue: thread = query (TMEM lane) =================
+            // quad = TMEM lane quadrant (= warp id % 4, a hardware rule), sub = which 64 columns of the buffer,
+            // half = pipeline group = which half page of every page
+            const int sub = (warp >> 2) & 1, half = warp >> 3;
+            uint64_t* myq = queues + (size_t)warp * kTcQueueCap;
+            volatile int* v_head = q_head + warp;
+            volatile float* v_tq = tq_s + qi;
+            int resv = 0;  // ring slots reserved and published by this warp so far (warp-uniform)
+            unsigned long long n_pairs = 0;
+            asm volatile("bar.sync %0, 160;" ::"r"(1 + quad) : "memory");  // the rescorer has published the initial bounds
+            float Tq = *v_tq;
+
+            // 32 columns: balanced min tree (FMNMX3, depth 4).  Rare path (some lane has a value under its bound): the lane
+            // finds its surviving columns through the tree's triple minima, reserves ring slots with one shared-memory
+            // atomic, writes them, and the warp publishes the new tail for the quadrant's rescorer.
+            auto process = [&](uint32_t (&v)[32], int col0) {
+                float m[11];
+#pragma unroll
+                for (int i = 0; i < 10; i++) m[i] = fminf(fminf(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1])), __uint_as_float(v[3 * i + 2]));
+                m[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+                float n0 = fminf(fminf(m[0], m[1]), m[2]), n1 = fminf(fminf(m[3], m[4]), m[5]), n2 = fminf(fminf(m[6], m[7]), m[8]),
+                      n3 = fminf(m[9], m[10]);
+                const float mn = fminf(fminf(fminf(n0, n1), n2), n3);
+                const bool hit = mn <= Tq;
+                if (__any_sync(0xffffffffu, hit)) {
+                    uint32_t mask = 0;
+                    if (hit) {
+#pragma unroll
+                        for (int i = 0; i < 11; i++) {
+                            if (m[i] <= Tq) {  // rare: look at the triple's columns
+#pragma unroll
+                                for (int u = 0; u < 3; u++)
+                                    if (3 * i + u < 32 && __uint_as_float(v[3 * i + u]) <= Tq) mask |= 1u << (3 * i + u);
+                            }
+                        }
+                    }
+                    // One round if the ring has room for everything (the common case: a handful of survivors); otherwise four
+                    // rounds of 8 columns (<= 256 = kTcQueueCap entries each).  The whole warp waits for room BEFORE any lane
+                    // reserves, so a full ring can always drain (only published entries are consumed).
+                    const int total_all = __reduce_add_sync(0xffffffffu, __popc(mask));
+                    const bool one_round = resv + total_all - *v_head <= kTcQueueCap;
+                    for (int h = 0; h < (one_round ? 1 : 4); h++) {
+                        uint32_t mq = one_round ? mask : (mask & (0xffu << (8 * h)));
+                        const int cnt = __popc(mq);
+                        const int total = one_round ? total_all : __reduce_add_sync(0xffffffffu, cnt);
+                        if (total == 0) continue;
+                        while (resv + total - *v_head > kTcQueueCap) __nanosleep(40);
+                        if (cnt) {
+                            int slot = atomicAdd(q_resv + warp, cnt);
+                            while (mq) {
+                                const int c = __ffs(mq) - 1;
+                                mq &= mq - 1;
+                                myq[(slot++) & (kTcQueueCap - 1)] = ((uint64_t)(uint32_t)lane << 32) | (uint32_t)(page * kPage + col0 + c);
+                            }
+                        }
+                        __syncwarp();
+                        __threadfence_block();
+                        resv += total;
+                        if (lane == 0) *reinterpret_cast<volatile int*>(q_tail + warp) = resv;  // publish for the rescorer
+                        __syncwarp();
+                    }
+                }
+            };
+
+            uint32_t pg = 0;
+            while (walk.next(page)) {
+                const uint32_t buf = 2 * (pg & 1) + half;
+                mbar_wait(&tfull_b[buf], (pg >> 1) & 1);
+                TC_STAMP(warp == 0, pg, 5);
+                tc_fence_after();
+                const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + buf * 128 + sub * 64;
+                const int col0 = half * 128 + sub * 64;
+                Tq = *v_tq;  // bound as last published by the rescorer (only ever tightens)
+                uint32_t va[32];
+                tmem_ld32(taddr, va);
+                tmem_ld_wait();
+                process(va, col0);
+                tmem_ld32(taddr + 32, va);
+                tmem_ld_wait();
+                // all of this warp's TMEM reads of the buffer are complete: hand it back to the MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_b[buf]);
+                TC_STAMP(warp == 0, pg, 6);
+                process(va, col0 + 32);
+                TC_STAMP(warp == 0, pg, 7);
+                if (half == 0 && sub == 0) n_pairs += (unsigned long long)min(kPage, T.n_points - page * kPage);
+                pg++;
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) *reinterpret_cast<volatile int*>(q_done + warp) = 1;
+            if (P.counters && half == 0 && sub == 0 && lane == 0) {
+                int nvalid = max(0, min(32, nq_tile - quad * 32));
                 atomicAdd(&P.counters[0], n_pairs * (unsigned long long)nvalid);
-                atomicAdd(&P.counters[1], (unsigned long long)n_exact);
-                atomicAdd(&P.counters[2], (unsigned long long)n_ins);
             }
         }
     }
