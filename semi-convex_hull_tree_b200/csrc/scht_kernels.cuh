@@ -587,20 +587,33 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
                             pos = page * kPage + in_page;
                             const float* pg = T.pages + (size_t)page * dpad * kPage + in_page;
                             const float* qq = qs + qw0 + qi;
-                            for (int j = 0; j < T.dim; j++) d2 = ref_acc_sq(d2, pg[(size_t)j * kPage] - qq[j * TQ]);
+                            // loads first (8 dims in flight), then the sequential reference chain: the chain would otherwise
+                            // serialise one L2 round trip per dimension
+                            for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                                float pv[8];
+#pragma unroll
+                                for (int u = 0; u < 8; u++) pv[u] = (j0 + u < T.dim) ? pg[(size_t)(j0 + u) * kPage] : 0.f;
+#pragma unroll
+                                for (int u = 0; u < 8; u++)
+                                    if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
+                            }
                             n_exact++;
                             cand = (d2 < 3.402823466e+38f) && (pos >= P.pos_lo) && (pos < P.pos_hi);
                         }
-                        unsigned m = __ballot_sync(0xffffffffu, cand);
-                        while (m) {
-                            int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            float cd2 = __shfl_sync(0xffffffffu, d2, src);
-                            int cpos = __shfl_sync(0xffffffffu, pos, src);
-                            uint32_t low = brute ? (uint32_t)T.orig_idx[cpos]
-                                                 : (((cpos >= a0 && cpos < a1) ? 0u : 0x80000000u) | (uint32_t)cpos);
-                            uint64_t key = ((uint64_t)__float_as_uint(cd2) << 32) | low;
-                            if (key < L[K - 1]) n_ins += list_insert(L, K, key, lane);
+                        // Smallest first: each round takes the warp-minimum key of the remaining candidates (two REDUX).  As soon as
+                        // the minimum cannot enter the list none of the others can, so rejected candidates cost nothing (while the
+                        // lists are still filling, most candidates of a batch are rejected by the ones inserted before them).
+                        uint32_t hi = cand ? __float_as_uint(d2) : 0xffffffffu;  // valid d2 bits are < 0x7f7fffff
+                        uint32_t low = 0xffffffffu;
+                        if (cand) low = brute ? (uint32_t)T.orig_idx[pos] : (((pos >= a0 && pos < a1) ? 0u : 0x80000000u) | (uint32_t)pos);
+                        for (;;) {
+                            const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+                            if (mhi == 0xffffffffu) break;
+                            const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? low : 0xffffffffu);
+                            const uint64_t key = ((uint64_t)mhi << 32) | mlo;
+                            if (key >= L[K - 1]) break;  // nothing smaller is left
+                            n_ins += list_insert(L, K, key, lane);
+                            if (hi == mhi && low == mlo) hi = 0xffffffffu;  // consumed (keys are unique)
                         }
                     } while (__any_sync(0xffffffffu, bits != 0));
                 }
