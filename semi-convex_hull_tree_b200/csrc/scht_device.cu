@@ -287,7 +287,8 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             const int page_lo = P.pos_lo / kPage, page_hi = (P.pos_hi + kPage - 1) / kPage;
             const double kept = (double)(after - before) / std::max(1.0, (double)sampled_q * std::max(1, page_hi - page_lo));
             TP.sel_mode = 2;
-            if (kept >= 0.90) {
+            // a prefilter page costs ~1/10 of an exact page, so pruning must remove much more before it pays for itself
+            if (kept >= (use_tc ? 0.60 : 0.90)) {
                 int rest = selection_size(n_tiles_main, 2, kSample);
                 k_list_all<<<(rest + 127) / 128, 128, 0, s>>>(h->ranges.as<int2>(), h->n_ranges.as<int>(), n_tiles_main, T.n_cuts, 2, kSample, page_lo,
                                                              page_hi);

@@ -687,7 +687,7 @@ struct TraverseParams {
 };
 
 __host__ __device__ inline size_t traverse_smem_bytes(int warps, int tq, int dpad) {
-    return (size_t)warps * ((size_t)dpad * tq * 4 + (size_t)kMaxLevel * tq * 4);
+    return (size_t)warps * ((size_t)dpad * tq * 4 + (size_t)kMaxLevel * tq * 4 + (size_t)(2 * dpad + 2 * kMaxLevel) * 4);
 }
 
 // i-th tile of a tile subset (see TraverseParams::sel_mode)
@@ -725,8 +725,12 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
     const int sel = (int)(job / T.n_cuts), cut = (int)(job % T.n_cuts);
     const int tile = tile_of_selection(sel, P.sel_mode, P.sel_step);
     if (tile >= n_tiles) return;
-    float* qs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((size_t)dpad * TQ + (size_t)kMaxLevel * TQ);  // [dpad][TQ]
-    float* dots = qs + (size_t)dpad * TQ;                                                                            // [level][TQ]
+    float* qs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((size_t)dpad * TQ + (size_t)kMaxLevel * TQ + 2 * dpad + 2 * kMaxLevel);  // [dpad][TQ]
+    float* dots = qs + (size_t)dpad * TQ;  // [level][TQ]
+    float* cen = dots + (size_t)kMaxLevel * TQ;  // [dpad] centroid of the tile's queries
+    float* cdots = cen + dpad;                   // [level] the centroid's dot memo
+    float* nrm_s = cdots + kMaxLevel;            // [dpad] the visited node's normal, staged once per node
+    float* beta_s = nrm_s + dpad;                // [level] the visited node's offsets
     const int q_begin = tile * P.tq;  // tile stride = the leaf-scan kernel's tile (<= TQ slots used)
     const int nq_tile = min(P.tq, P.nq - q_begin);
 
@@ -756,6 +760,39 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
         }
     }
     __syncwarp();
+    // Bounding ball of the tile's queries (centre = centroid, radius r): the bound of a node is 1-Lipschitz in the query
+    // (its normals have unit length), so bound(q) >= bound(centre) - r for every query of the tile.  One centre test
+    // prunes a subtree for all queries at 1/(32*QL) of the cost of the per-query tests; those run only when it fails.
+    float r_tile = 0.f, k_max = 0.f, absm_c = 0.f;
+    {
+        for (int j = 0; j < dpad; j++) {
+            float sj = 0.f;
+#pragma unroll
+            for (int u = 0; u < QL; u++) sj += valid[u] ? qs[j * TQ + lane + 32 * u] : 0.f;
+            for (int o = 16; o; o >>= 1) sj += __shfl_xor_sync(0xffffffffu, sj, o);
+            if (lane == 0) cen[j] = sj / (float)nq_tile;
+        }
+        __syncwarp();
+        float cn2 = 0.f;
+        for (int j = 0; j < dpad; j++) cn2 = fmaf(cen[j], cen[j], cn2);
+#pragma unroll
+        for (int u = 0; u < QL; u++) {
+            if (!valid[u]) continue;
+            float d2 = 0.f;
+            for (int j = 0; j < dpad; j++) {
+                float d = qs[j * TQ + lane + 32 * u] - cen[j];
+                d2 = fmaf(d, d, d2);
+            }
+            r_tile = fmaxf(r_tile, d2);
+            k_max = fmaxf(k_max, thr2[u]);
+        }
+        for (int o = 16; o; o >>= 1) {
+            r_tile = fmaxf(r_tile, __shfl_xor_sync(0xffffffffu, r_tile, o));
+            k_max = fmaxf(k_max, __shfl_xor_sync(0xffffffffu, k_max, o));
+        }
+        r_tile = sqrtf(r_tile) * 1.0001f + 1e-30f;
+        absm_c = 16.f * (float)(T.dim + 2) * 5.9604645e-8f * (sqrtf(cn2) * 1.0001f + T.xnorm_max);
+    }
 
     int2* out = P.ranges + ((size_t)tile * kMaxCuts + cut) * kJobRanges;
     int n_out = 0, cur_b = -1, cur_e = -1;  // open range [cur_b, cur_e)
@@ -781,12 +818,36 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
         const int k = nr.depth;
         const float* nrm = T.node_normal + (size_t)n * dpad;
         const float* beta = T.node_beta + nr.beta_off;
+        {
+            // centre test: lanes over dimensions for the dot, lanes over constraints for the bound
+            // (the node's normal and offsets are read from global memory once, coalesced, and staged in shared memory:
+            // the per-query loops below would otherwise expose one L1/L2 round trip per element)
+            float part = 0.f;
+            for (int j = lane; j < dpad; j += 32) {
+                const float a = nrm[j];
+                nrm_s[j] = a;
+                part = fmaf(a, cen[j], part);
+            }
+            const int kc = min(k, kMaxLevel);  // kMaxLevel == 32: one constraint per lane
+            const float my_beta = (lane < kc) ? beta[lane] : 0.f;
+            beta_s[lane] = my_beta;
+            for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (k <= kMaxLevel && lane == 0) cdots[k - 1] = part;
+            __syncwarp();
+            float t = (lane < kc) ? fmaxf(-(cdots[lane] + my_beta), 0.f) : 0.f;
+            const float lbc = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(t)));
+            const float safe_c = lbc * 0.9999f - absm_c - r_tile * 1.0001f;
+            if (safe_c > 0.f && safe_c * safe_c > k_max) {
+                tests += 1;
+                return true;
+            }
+        }
 #pragma unroll
         for (int u = 0; u < QL; u++) {
             int qi = lane + 32 * u;
             float d0 = 0.f, d1 = 0.f;
             for (int j = 0; j < dpad; j += 4) {
-                float4 a = *reinterpret_cast<const float4*>(nrm + j);
+                float4 a = *reinterpret_cast<const float4*>(nrm_s + j);
                 d0 = fmaf(a.x, qs[(j + 0) * TQ + qi], d0);
                 d1 = fmaf(a.y, qs[(j + 1) * TQ + qi], d1);
                 d0 = fmaf(a.z, qs[(j + 2) * TQ + qi], d0);
@@ -798,10 +859,10 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
             const int kk = min(k, kMaxLevel);
             int j = 0;
             for (; j + 1 < kk; j += 2) {
-                lb0 = fmaxf(lb0, -(dots[j * TQ + qi] + beta[j]));
-                lb1 = fmaxf(lb1, -(dots[(j + 1) * TQ + qi] + beta[j + 1]));
+                lb0 = fmaxf(lb0, -(dots[j * TQ + qi] + beta_s[j]));
+                lb1 = fmaxf(lb1, -(dots[(j + 1) * TQ + qi] + beta_s[j + 1]));
             }
-            if (j < kk) lb0 = fmaxf(lb0, -(dots[j * TQ + qi] + beta[j]));
+            if (j < kk) lb0 = fmaxf(lb0, -(dots[j * TQ + qi] + beta_s[j]));
             const float safe = fmaxf(lb0, lb1) * 0.9999f - absm[u];
             const bool prune = !valid[u] || ((safe > 0.f) && (safe * safe > thr2[u]));
             prune_all &= prune;

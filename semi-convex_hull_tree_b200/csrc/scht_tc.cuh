@@ -149,7 +149,8 @@ __device__ __forceinline__ float tc_margin(float abs_sum_pmax, float qnorm, floa
 }
 
 // eligibility: the prefilter pays off when its error margin is small against the K-th distance after the seed scan.
-// counters[6] += queries whose margin is below 1/16 of the seed K-th distance^2 (and which fit FP16's range)
+// counters[6] += queries whose margin is below 1/4 of the seed K-th distance^2 (and which fit FP16's range): even then
+// the survivors are a tiny fraction of the pairs, and a prefilter page costs ~1/10 of an exact page
 __global__ void k_tc_eligibility(DevTree T, const float* __restrict__ q, const int* __restrict__ q_order, int nq, int K,
                                  const uint64_t* __restrict__ state, const float* __restrict__ mean, const float* __restrict__ pmax,
                                  float pnorm_max, float pabs_sum, float scale, unsigned long long* __restrict__ counters) {
@@ -167,7 +168,7 @@ __global__ void k_tc_eligibility(DevTree T, const float* __restrict__ q, const i
         }
         float margin = tc_margin(s1 * 1.0001f, sqrtf(n2) * 1.0001f, l1 * 1.0001f, pnorm_max, pabs_sum, scale);
         float kth = __uint_as_float((uint32_t)(state[(size_t)slot * K + K - 1] >> 32));
-        ok = (kth < 3.0e38f) && (margin * 16.f <= kth) && (2.f * amax * scale < 60000.f);
+        ok = (kth < 3.0e38f) && (margin * 4.f <= kth) && (2.f * amax * scale < 60000.f);
     }
     unsigned m = __ballot_sync(0xffffffffu, ok);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[6], (unsigned long long)__popc(m));
