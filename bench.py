@@ -13,7 +13,6 @@ roofline: leaf-scan kernel: algorithmic bytes (points the REFERENCE algorithm sc
 cpu_baseline: the reference (oracle/_ref/ref_knn, kind "reference") or the C oracle (kind "port") on a bounded query sample
 """
 import argparse
-import ctypes
 import importlib
 import json
 import os
@@ -34,6 +33,8 @@ WORKLOADS = {
     "uniform_1Mx16_q100k_K10": (1_000_000, 16, 100_000, 10, 0.0005, "uniform"),
     "gauss_10Mx32_q1M_K10": (10_000_000, 32, 1_000_000, 10, 0.00005, "gauss1000"),
     "gauss_2Mx32_q200k_K10": (2_000_000, 32, 200_000, 10, 0.00025, "gauss1000"),
+    "gauss_2Mx32_q200k_K100": (2_000_000, 32, 200_000, 100, 0.00025, "gauss1000"),
+    "gauss_2Mx32_q200k_K1": (2_000_000, 32, 200_000, 1, 0.00025, "gauss1000"),
     "siftlike_1Mx128_q100k_K10": (1_000_000, 128, 100_000, 10, 0.0005, "sift"),
     "posture_like_78095x15_self_K10": (78_095, 15, 78_095, 10, 0.005, "posture"),
     "smoke_50kx16_q4k_K10": (50_000, 16, 4_096, 10, 0.005, "uniform"),

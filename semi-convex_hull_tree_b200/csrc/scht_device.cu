@@ -76,7 +76,7 @@ struct scht_handle {
     float pnorm_max = 0.f;
     int64_t tc_batches = 0;
     std::vector<int> h_leaf_start, h_leaf_count;
-    DevBuf q, q_leaf, hist, q_order, state, ranges, n_ranges, idx, d2, dist, counters, leaf_tmp;
+    DevBuf q, q_leaf, hist, q_order, state, ranges, n_ranges, idx, d2, dist, counters;
 };
 
 namespace {
@@ -237,7 +237,9 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         if (timed) CU_TRY(cudaEventRecord(h->ev[2], s));
         // tensor-core prefilter or exact FP32 scan for the main pass?
         bool use_tc = false;
-        if (h->kp > 0 && h->tc_mode != 0 && (int)tc_smem_bytes(T.dpad, h->kp, K) <= h->max_smem) {
+        int tc_stages = kTcMaxStages;
+        while (tc_stages > 3 && (int)tc_smem_bytes(T.dpad, h->kp, K, tc_stages) > h->max_smem) tc_stages--;
+        if (h->kp > 0 && h->tc_mode != 0 && (int)tc_smem_bytes(T.dpad, h->kp, K, tc_stages) <= h->max_smem) {
             if (h->tc_mode == 1) {
                 use_tc = true;
             } else {
@@ -320,13 +322,14 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             TC.scale = h->tc_scale;
             TC.norm_unit = h->norm_unit;
             TC.kp = h->kp;
+            TC.n_stages = tc_stages;
 #ifdef SCHT_TC_PROF
             static long long* d_trace = nullptr;
             if (!d_trace) cudaMalloc(&d_trace, 64 * 8 * 8);
             cudaMemsetAsync(d_trace, 0, 64 * 8 * 8, s);
             TC.trace = d_trace;
 #endif
-            size_t smem = tc_smem_bytes(T.dpad, h->kp, K);
+            size_t smem = tc_smem_bytes(T.dpad, h->kp, K, tc_stages);
             CU_TRY(cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_scan_tc<<<n_tiles_main, kTcThreads, smem, s>>>(TC);
             CU_TRY(cudaGetLastError());
@@ -690,7 +693,7 @@ extern "C" void scht_destroy(scht_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->owned) cudaFree(p);
-    for (DevBuf* b : {&h->q, &h->q_leaf, &h->hist, &h->q_order, &h->state, &h->ranges, &h->n_ranges, &h->idx, &h->d2, &h->dist, &h->counters, &h->leaf_tmp})
+    for (DevBuf* b : {&h->q, &h->q_leaf, &h->hist, &h->q_order, &h->state, &h->ranges, &h->n_ranges, &h->idx, &h->d2, &h->dist, &h->counters})
         b->release();
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);

@@ -37,7 +37,7 @@ namespace scht {
 
 constexpr int kTcQ = 128;          // queries per tile (MMA M)
 constexpr int kTcKSlice = 32;      // K elements (FP16) per shared-memory stage: 16 KB
-constexpr int kTcStages = 6;       // slice stages
+constexpr int kTcMaxStages = 6;    // slice stages (fewer when K is large and the lists need the shared memory)
 constexpr int kTcEpiWarps = 16;
 constexpr int kTcThreads = (kTcEpiWarps + 1 + 4 + 4) * 32;  // + producer, 4 MMA issuers, 4 rescorers
 constexpr int kTcQueueCap = 256;   // ring entries per epilogue warp (power of two)
@@ -52,14 +52,15 @@ struct TcScanParams {
     float scale;             // s (power of two)
     float norm_unit;         // power of two u: the norm slots hold s^2|p'|^2 / u, the query operand holds u
     int kp;                  // padded K (multiple of 16) = ceil16(dim + 3)
+    int n_stages;            // slice stages in shared memory (3..kTcMaxStages)
     long long* trace;        // SCHT_TC_PROF builds: [64 pages][8] clock64 stamps of tile 0 (pages 2000..2063)
 };
 
 __host__ __device__ inline size_t tc_page_bytes(int kp) { return (size_t)kp * 512; }
 
-__host__ __device__ inline size_t tc_smem_bytes(int dpad, int kp, int K) {
+__host__ __device__ inline size_t tc_smem_bytes(int dpad, int kp, int K, int n_stages) {
     size_t b = 1024;                                                         // alignment slack
-    b += (size_t)kTcStages * (kp < kTcKSlice ? kp : kTcKSlice) * 512;        // B slice stages (<= 16 KB each)
+    b += (size_t)n_stages * (kp < kTcKSlice ? kp : kTcKSlice) * 512;         // B slice stages (<= 16 KB each)
     b += (size_t)kTcQ * kp * 2;                                              // A operand
     b += (size_t)kTcQ * K * 8;                                               // lists
     b += (size_t)kTcEpiWarps * kTcQueueCap * 8;                              // candidate queues
@@ -186,15 +187,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     const int stage_k = min(kp, kTcKSlice);                                    // K elements held by one stage
     const uint32_t stage_bytes = (uint32_t)stage_k * 512;
     unsigned char* stage_mem = base;                                           // [stages][stage_k/8][32][8][8] halves
-    __half* sA = reinterpret_cast<__half*>(stage_mem + (size_t)kTcStages * stage_bytes);  // [kp/8][16][8][8]
+    const int n_stages = TP.n_stages;
+    __half* sA = reinterpret_cast<__half*>(stage_mem + (size_t)n_stages * stage_bytes);  // [kp/8][16][8][8]
     uint64_t* lists = reinterpret_cast<uint64_t*>(sA + (size_t)kTcQ * kp);     // [128][K]
     uint64_t* queues = lists + (size_t)kTcQ * K;                               // [16][kTcQueueCap]
     int* a0s = reinterpret_cast<int*>(queues + (size_t)kTcEpiWarps * kTcQueueCap);
     int* a1s = a0s + kTcQ;
     int* qids = a1s + kTcQ;
     uint64_t* full_b = reinterpret_cast<uint64_t*>(qids + kTcQ);
-    uint64_t* empty_b = full_b + kTcStages;
-    uint64_t* tfull_b = empty_b + kTcStages;      // [4]
+    uint64_t* empty_b = full_b + kTcMaxStages;
+    uint64_t* tfull_b = empty_b + kTcMaxStages;   // [4]
     uint64_t* tempty_b = tfull_b + 4;             // [4]
     int* q_tail = reinterpret_cast<int*>(tempty_b + 4);  // [16] entries pushed (written by the epilogue warp)
     int* q_head = q_tail + kTcEpiWarps;                  // [16] entries consumed (written by the rescorer)
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
 
     // ---- set-up ---------------------------------------------------------------------------------------------
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; s++) {
+        for (int s = 0; s < n_stages; s++) {
             mbar_init(&full_b[s], 1);
             mbar_init(&empty_b[s], 2);  // one commit per MMA warp
         }
@@ -279,8 +281,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
             while (walk.next(page)) {
                 const unsigned char* src = TP.tcpages + (size_t)page * page_bytes;
                 for (int s = 0; s < n_slices; s++, it++) {
-                    const uint32_t st = it % kTcStages;
-                    const uint32_t ph = (it / kTcStages) & 1;
+                    const uint32_t st = it % (uint32_t)n_stages;
+                    const uint32_t ph = (it / (uint32_t)n_stages) & 1;
                     mbar_wait(&empty_b[st], ph ^ 1);
                     TC_STAMP(s == 0, ppg, 0);
                     const uint32_t bytes = (uint32_t)min(kTcKSlice, kp - s * kTcKSlice) * 512;
@@ -323,8 +325,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
             mbar_wait(&tempty_b[buf], ((pg >> 1) & 1) ^ 1);
             TC_STAMP(g == 0, pg, 2);
             for (int s = 0; s < n_slices; s++, it++) {
-                const uint32_t st = it % kTcStages;
-                const uint32_t ph = (it / kTcStages) & 1;
+                const uint32_t st = it % (uint32_t)n_stages;
+                const uint32_t ph = (it / (uint32_t)n_stages) & 1;
                 mbar_wait(&full_b[st], ph);
                 TC_STAMP(g == 0 && s == 0, pg, 3);
                 tc_fence_after();

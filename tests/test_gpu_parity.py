@@ -208,3 +208,38 @@ def test_prefilter_on_and_off(pkg, orc, monkeypatch, tc, n, dim, nq, K, pct, kin
     assert_bit_equal(d2, od2, "dist2")
     assert_bit_equal(d, od, "dist")
     ix.close()
+
+
+@pytest.mark.parametrize("env", [{"SCHT_SCAN_VARIANT": "0"}, {"SCHT_SCAN_VARIANT": "1"}, {"SCHT_SCAN_VARIANT": "2"},
+                                 {"SCHT_TRAVERSE_SAMPLING": "0"}, {"SCHT_TRAVERSE_SAMPLING": "0", "SCHT_TC": "1"}])
+def test_kernel_variants_and_knobs(pkg, orc, monkeypatch, env):
+    """every leaf-scan kernel variant (8/7/4 consumer warps) and the traversal with sampling switched off give the
+    reference's bits (the knobs only change the schedule)"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(77)
+    n, nq, K = 50000, 9000, 10  # 9000 queries: enough tiles for the sampled traversal to engage when it is on
+    for dim, data, q in ((16, rng.random((n, 16), dtype=np.float32), rng.random((nq, 16), dtype=np.float32)),
+                         (20, clusters(rng, n, 20, 40, 0.05), clusters(rng, nq, 20, 40, 0.05))):
+        ht = pkg.HostTree(data, 0.004, seed=1)
+        oi, od2, _, _, _ = orc.knn(ht, q, K, alg=2)
+        ix = pkg.Index(ht)
+        idx, d2, st = ix.query(q, K, want_stats=True)
+        assert_bit_equal(idx, oi, "idx dim=%d" % dim)
+        assert_bit_equal(d2, od2, "dist2 dim=%d" % dim)
+        if env.get("SCHT_TC") == "1":
+            assert st["prefilter_batches"] == 1
+        ix.close()
+
+
+def test_stats_surface(pkg):
+    """the statistics the reference prints (Code/GPU_Convex_Tree.h:950-971) are filled in"""
+    rng = np.random.default_rng(5)
+    data, q = rng.random((30000, 8), dtype=np.float32), rng.random((3000, 8), dtype=np.float32)
+    ix = pkg.Index(pkg.HostTree(data, 0.005, seed=1))
+    ix.set_batch_size(1000)
+    _, _, st = ix.query(q, 10, want_stats=True)
+    assert st["n_queries"] == 3000 and st["batches"] == 3 and st["kernel_launches"] >= 21
+    assert st["dist_computations"] > 0 and st["hyperplane_tests"] > 0 and st["descent_dists"] > 0 and st["list_insertions"] >= 30000
+    assert st["ms_total"] >= st["ms_device"] > 0 and abs(st["ms_scan"] - st["ms_seed_scan"] - st["ms_main_scan"]) < 1e-3
+    ix.close()
