@@ -271,6 +271,7 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         TP.leaf_lo = leaf_lo;
         TP.leaf_hi = leaf_hi;
         TP.counters = ctr;
+        TP.ball_only = use_tc ? 1 : 0;
         // Sampled first: when the bounds keep >= 90 % of the pages for every 8th tile, they are not evaluated for the
         // other tiles (all their pages are listed); otherwise the remaining tiles are traversed too.
         // (about 24 sampled tiles, at least every 64th and at most every 8th tile)

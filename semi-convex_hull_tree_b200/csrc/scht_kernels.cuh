@@ -683,6 +683,8 @@ struct TraverseParams {
     int* n_ranges;           // [n_tiles][kMaxCuts]
     int leaf_lo, leaf_hi;    // only leaves in [leaf_lo, leaf_hi) are emitted (sharded-dataset mode)
     int sel_mode, sel_step;  // tile subset: 0 all tiles, 1 tiles with t % step == 0 (sample), 2 the other tiles
+    int ball_only;           // 1: only the bounding-ball test (prefilter scan: a per-query test of a leaf costs about as
+                             //    much as letting the tensor core scan its page, so only the ~free tile-level test is used)
     unsigned long long* counters;  // [4] node tests (per query), [5] pages listed
 };
 
@@ -837,10 +839,9 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
             float t = (lane < kc) ? fmaxf(-(cdots[lane] + my_beta), 0.f) : 0.f;
             const float lbc = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(t)));
             const float safe_c = lbc * 0.9999f - absm_c - r_tile * 1.0001f;
-            if (safe_c > 0.f && safe_c * safe_c > k_max) {
-                tests += 1;
-                return true;
-            }
+            tests += 1;
+            if (safe_c > 0.f && safe_c * safe_c > k_max) return true;
+            if (P.ball_only) return false;
         }
 #pragma unroll
         for (int u = 0; u < QL; u++) {
