@@ -103,6 +103,16 @@ const scht_tree_desc* scht_host_tree_desc(const scht_host_tree* tree);
 double scht_host_tree_build_seconds(const scht_host_tree* tree);
 void scht_host_tree_free(scht_host_tree* tree);
 
+/* Same construction executed on one B200: a persistent cooperative kernel walks the
+ * reference's DFS (build_tree, Code/Convex_Tree.h:708-857) node by node — the rand() stream forces that
+ * order — and parallelises the work inside each node (pivot distances, getBeta_1 re-tightening
+ * :563-589, stable partition :809-821).  The arithmetic is the reference's, so the resulting
+ * scht_host_tree is BIT-IDENTICAL to scht_build_tree's for the same data and seed.  Needs an sm_100
+ * device (SCHT_ERR_NO_DEVICE otherwise; there is no silent fallback to the host builder) and
+ * 2*N*D*4 + 13*N bytes of device memory; trees deeper than 64 levels -> SCHT_ERR_INVALID_ARG. */
+int scht_build_tree_device(const float* data, int64_t n_points, int32_t dim, float leaf_pts_percent,
+                           uint32_t rand_seed, int32_t device, scht_host_tree** out);
+
 /* ------------------------------------------------------------------------------------------------
  * Device tree + query.  Replaces GPU_Convex_Tree<T>'s constructor tail
  * (init_openCL_device / init_openCL_sorted_data_set, Code/GPU_Convex_Tree.h:150-163,431-479,522-748)

@@ -53,6 +53,7 @@ class SchtError(RuntimeError):
 # every symbol include/scht.h declares: (restype, argtypes)
 SYMBOLS = {
     "scht_build_tree": (C.c_int, [f32p, C.c_int64, C.c_int32, C.c_float, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "scht_build_tree_device": (C.c_int, [f32p, C.c_int64, C.c_int32, C.c_float, C.c_uint32, C.c_int32, C.POINTER(C.c_void_p)]),
     "scht_host_tree_desc": (C.POINTER(TreeDesc), [C.c_void_p]),
     "scht_host_tree_build_seconds": (C.c_double, [C.c_void_p]),
     "scht_host_tree_free": (None, [C.c_void_p]),
@@ -117,16 +118,22 @@ def _np(ptr, shape, dtype):
 
 
 class HostTree:
-    """Host-built tree (scht_build_tree): the reference's constructor path, Code/Convex_Tree.h:518-548."""
+    """Built tree in host memory: the reference's constructor path, Code/Convex_Tree.h:518-548.  `device=None` runs the
+    host builder (scht_build_tree); `device=i` runs the same construction on GPU i (scht_build_tree_device) — the
+    arrays are bit-identical either way."""
 
-    def __init__(self, data, leaf_pts_percent, seed=1):
+    def __init__(self, data, leaf_pts_percent, seed=1, device=None):
         data = np.ascontiguousarray(data, dtype=np.float32)
         if data.ndim != 2:
             raise ValueError("data must be [n, dim]")
         self._h = C.c_void_p()
         self.data = data
-        _check(lib().scht_build_tree(data.ctypes.data_as(f32p), data.shape[0], data.shape[1], float(leaf_pts_percent), int(seed),
-                                     C.byref(self._h)))
+        if device is None:
+            _check(lib().scht_build_tree(data.ctypes.data_as(f32p), data.shape[0], data.shape[1], float(leaf_pts_percent),
+                                         int(seed), C.byref(self._h)))
+        else:
+            _check(lib().scht_build_tree_device(data.ctypes.data_as(f32p), data.shape[0], data.shape[1],
+                                                float(leaf_pts_percent), int(seed), int(device), C.byref(self._h)))
         self.desc = lib().scht_host_tree_desc(self._h)
         self.build_seconds = lib().scht_host_tree_build_seconds(self._h)
 

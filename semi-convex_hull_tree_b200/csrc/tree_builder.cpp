@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "scht_error.h"
+#include "scht_host_tree.h"
 
 namespace {
 
@@ -220,12 +221,6 @@ struct Builder {
 
 }  // namespace
 
-struct scht_host_tree {
-    scht_tree_desc desc;
-    double build_seconds;
-    std::vector<float> sorted_points, left_center, right_center, normal, beta;
-    std::vector<int32_t> sorted_to_orig, leaf_start, leaf_count, leaf_node_id, left, right, parent, leaf_index, beta_off;
-};
 
 extern "C" int scht_build_tree(const float* data, int64_t n_points, int32_t dim, float leaf_pts_percent,
                                uint32_t rand_seed, scht_host_tree** out) {
