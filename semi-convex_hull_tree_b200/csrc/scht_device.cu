@@ -329,6 +329,7 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             if (!d_trace) cudaMalloc(&d_trace, 64 * 8 * 8);
             cudaMemsetAsync(d_trace, 0, 64 * 8 * 8, s);
             TC.trace = d_trace;
+            if (const char* ev = getenv("SCHT_TC_DEBUG")) TC.debug = atoi(ev);
 #endif
             size_t smem = tc_smem_bytes(T.dpad, h->kp, K, tc_stages);
             CU_TRY(cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -80,17 +80,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the hint (ns) expires: a long hint keeps waiting
+// warps from re-issuing the poll (they share issue slots with the warps doing the work)
+constexpr uint32_t kMbarSuspendNs = 20000;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(kMbarSuspendNs)
         : "memory");
 }
 // Producer-side wait: the producer lane is normally several stages ahead, so it polls with a sleep in between instead

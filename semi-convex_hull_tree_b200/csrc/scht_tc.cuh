@@ -53,6 +53,7 @@ struct TcScanParams {
     float norm_unit;         // power of two u: the norm slots hold s^2|p'|^2 / u, the query operand holds u
     int kp;                  // padded K (multiple of 16) = ceil16(dim + 3)
     int n_stages;            // slice stages in shared memory (3..kTcMaxStages)
+    int debug;               // SCHT_TC_PROF builds only: 1 = no pair passes the filter, 2 = also skip the min tree
     long long* trace;        // SCHT_TC_PROF builds: [64 pages][8] clock64 stamps of tile 0 (pages 2000..2063)
 };
 
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                     v_tq[qi] = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));
                 }
                 if (all_done) break;
-                if (!did_work) __nanosleep(100);
+                if (!did_work) __nanosleep(1000);
             }
             __syncwarp();
             // ---- results: the rescorer owns the lists of its 32 queries ----
@@ -501,6 +502,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
             // finds its surviving columns through the tree's triple minima, reserves ring slots with one shared-memory
             // atomic, writes them, and the warp publishes the new tail for the quadrant's rescorer.
             auto process = [&](uint32_t (&v)[32], int col0) {
+#ifdef SCHT_TC_PROF
+                if (TP.debug == 2) return;
+#endif
                 float m[11];
 #pragma unroll
                 for (int i = 0; i < 10; i++) m[i] = fminf(fminf(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1])), __uint_as_float(v[3 * i + 2]));
@@ -508,7 +512,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                 float n0 = fminf(fminf(m[0], m[1]), m[2]), n1 = fminf(fminf(m[3], m[4]), m[5]), n2 = fminf(fminf(m[6], m[7]), m[8]),
                       n3 = fminf(m[9], m[10]);
                 const float mn = fminf(fminf(fminf(n0, n1), n2), n3);
+#ifdef SCHT_TC_PROF
+                const bool hit = (TP.debug == 0) && mn <= Tq;
+#else
                 const bool hit = mn <= Tq;
+#endif
                 if (__any_sync(0xffffffffu, hit)) {
                     uint32_t mask = 0;
                     if (hit) {
