@@ -179,12 +179,25 @@ __global__ void k_tc_eligibility(DevTree T, const float* __restrict__ q, const i
 // -------------------------------------------------------------------------------------------------------------
 // the prefilter scan kernel
 // -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmin3f(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// asm so that the compiler does not re-fuse pairs of 2-input minima into FMNMX3
+__device__ __forceinline__ float fmin2f(float a, float b) {
+    float d;
+    asm("min.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
 __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP) {
     const ScanParams& P = TP.S;
     const DevTree& T = P.T;
     const int dpad = T.dpad, K = P.K, kp = TP.kp;
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    // (no manual re-alignment: the no-swizzle UMMA layout and cp.async.bulk need 16 bytes only, and a pointer that is
+    // visibly derived from the __shared__ array keeps every access below an LDS/STS/ATOMS instead of a generic LD/ST/ATOM)
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    unsigned char* base = smem_dyn;
     const int stage_k = min(kp, kTcKSlice);                                    // K elements held by one stage
     const uint32_t stage_bytes = (uint32_t)stage_k * 512;
     unsigned char* stage_mem = base;                                           // [stages][stage_k/8][32][8][8] halves
@@ -277,13 +290,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     if (warp == kTcEpiWarps) {
         // ================= producer: the whole warp walks, one elected lane issues the bulk copies =================
         {
-            uint32_t it = 0, ppg = 0;
+            uint32_t st = 0, ph = 0, ppg = 0;  // stage ring position, kept incrementally (a division per page would sit on this warp's critical path)
             const size_t page_bytes = tc_page_bytes(kp);
             while (walk.next(page)) {
                 const unsigned char* src = TP.tcpages + (size_t)page * page_bytes;
-                for (int s = 0; s < n_slices; s++, it++) {
-                    const uint32_t st = it % (uint32_t)n_stages;
-                    const uint32_t ph = (it / (uint32_t)n_stages) & 1;
+                for (int s = 0; s < n_slices; s++) {
                     mbar_wait(&empty_b[st], ph ^ 1);
                     TC_STAMP(s == 0, ppg, 0);
                     const uint32_t bytes = (uint32_t)min(kTcKSlice, kp - s * kTcKSlice) * 512;
@@ -292,6 +303,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                         bulk_g2s(stage_mem + (size_t)st * stage_bytes, src + (size_t)s * kTcKSlice * 512, bytes, &full_b[st]);
                     }
                     __syncwarp();
+                    if (++st == (uint32_t)n_stages) {
+                        st = 0;
+                        ph ^= 1;
+                    }
                 }
                 TC_STAMP(true, ppg, 1);
                 ppg++;
@@ -313,10 +328,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
         const uint32_t kBStage = stage_bytes / 16;
         const uint64_t da0 = umma_desc_kmajor(smem_u32(sA), (kTcQ / 8) * 128, 128);
         const uint64_t db0 = umma_desc_kmajor(smem_u32(stage_mem), (kPage / 8) * 128, 128) + (uint64_t)((uint32_t)g * kBHalf);
-        uint32_t it = 0, pg = 0;
+        uint32_t st = 0, ph = 0, pg = 0;
+        auto advance = [&](uint32_t k) {
+            st += k;
+            while (st >= (uint32_t)n_stages) {
+                st -= (uint32_t)n_stages;
+                ph ^= 1;
+            }
+        };
         while (walk.next(page)) {
             if ((int)(pg & 1) != my_par) {  // the other parity's issuer handles this page
-                it += n_slices;
+                advance((uint32_t)n_slices);
                 pg++;
                 continue;
             }
@@ -325,9 +347,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
             const uint32_t d_tmem = tmem + buf * kHalf;
             mbar_wait(&tempty_b[buf], ((pg >> 1) & 1) ^ 1);
             TC_STAMP(g == 0, pg, 2);
-            for (int s = 0; s < n_slices; s++, it++) {
-                const uint32_t st = it % (uint32_t)n_stages;
-                const uint32_t ph = (it / (uint32_t)n_stages) & 1;
+            for (int s = 0; s < n_slices; s++) {
                 mbar_wait(&full_b[st], ph);
                 TC_STAMP(g == 0 && s == 0, pg, 3);
                 tc_fence_after();
@@ -343,6 +363,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                     umma_commit(&empty_b[st]);  // the stage may be refilled once both half pages' MMAs have read it
                 }
                 __syncwarp();
+                advance(1);
             }
             TC_STAMP(g == 0, pg, 4);
             pg++;
@@ -450,7 +471,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                     v_tq[qi] = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));
                 }
                 if (all_done) break;
-                if (!did_work) __nanosleep(1000);
+                if (!did_work) __nanosleep(4000);  // survivors are rare (~1 per 10 pages and warp): poll seldom, the pipeline warps need the issue slots
             }
             __syncwarp();
             // ---- results: the rescorer owns the lists of its 32 queries ----
@@ -498,34 +519,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
             asm volatile("bar.sync %0, 160;" ::"r"(1 + quad) : "memory");  // the rescorer has published the initial bounds
             float Tq = *v_tq;
 
-            // 32 columns: balanced min tree (FMNMX3, depth 4).  Rare path (some lane has a value under its bound): the lane
-            // finds its surviving columns through the tree's triple minima, reserves ring slots with one shared-memory
+            // 32 columns: min tree over four groups of 8.  Rare path (some lane has a value under its bound): the lane
+            // finds its surviving columns through the group minima, reserves ring slots with one shared-memory
             // atomic, writes them, and the warp publishes the new tail for the quadrant's rescorer.
             auto process = [&](uint32_t (&v)[32], int col0) {
 #ifdef SCHT_TC_PROF
                 if (TP.debug == 2) return;
 #endif
-                float m[11];
+                // four groups of 8: 2 FMNMX3 (ALU pipe, half rate) + 3 FMNMX (FMA pipe, full rate) each, so both pipes work
+                float m[4];
 #pragma unroll
-                for (int i = 0; i < 10; i++) m[i] = fminf(fminf(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1])), __uint_as_float(v[3 * i + 2]));
-                m[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-                float n0 = fminf(fminf(m[0], m[1]), m[2]), n1 = fminf(fminf(m[3], m[4]), m[5]), n2 = fminf(fminf(m[6], m[7]), m[8]),
-                      n3 = fminf(m[9], m[10]);
-                const float mn = fminf(fminf(fminf(n0, n1), n2), n3);
-#ifdef SCHT_TC_PROF
-                const bool hit = (TP.debug == 0) && mn <= Tq;
-#else
+                for (int g = 0; g < 4; g++) {
+                    const float x = fmin3f(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
+                    const float y = fmin3f(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+                    const float z = fmin2f(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+                    m[g] = fmin2f(fmin2f(x, y), z);
+                }
+                const float mn = fmin2f(fmin2f(m[0], m[1]), fmin2f(m[2], m[3]));
                 const bool hit = mn <= Tq;
-#endif
                 if (__any_sync(0xffffffffu, hit)) {
                     uint32_t mask = 0;
                     if (hit) {
 #pragma unroll
-                        for (int i = 0; i < 11; i++) {
-                            if (m[i] <= Tq) {  // rare: look at the triple's columns
+                        for (int g = 0; g < 4; g++) {
+                            if (m[g] <= Tq) {  // rare: look at the group's columns
 #pragma unroll
-                                for (int u = 0; u < 3; u++)
-                                    if (3 * i + u < 32 && __uint_as_float(v[3 * i + u]) <= Tq) mask |= 1u << (3 * i + u);
+                                for (int u = 0; u < 8; u++)
+                                    if (__uint_as_float(v[8 * g + u]) <= Tq) mask |= 1u << (8 * g + u);
                             }
                         }
                     }
