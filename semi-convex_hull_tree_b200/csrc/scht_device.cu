@@ -576,10 +576,12 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     {
         // seed neighbourhood of every leaf: the smallest enclosing subtree with >= kSeedPoints points
         std::vector<int> ss(L), se(L);
+        int seed_points = kSeedPoints;
+        if (const char* ev = getenv("SCHT_SEED_POINTS")) seed_points = std::max(1, atoi(ev));
         for (int i = 0; i < nn; i++) {
             if (rec[i].leaf < 0) continue;
             int a = i;
-            while (rec[a].pos1 - rec[a].pos0 < kSeedPoints && t->node_parent[a] >= 0) a = t->node_parent[a];
+            while (rec[a].pos1 - rec[a].pos0 < seed_points && t->node_parent[a] >= 0) a = t->node_parent[a];
             ss[rec[i].leaf] = rec[a].pos0;
             se[rec[i].leaf] = rec[a].pos1;
         }

@@ -30,7 +30,10 @@ constexpr int kRowsPerStage = 16;  // dims per shared-memory stage (16 rows x 25
 constexpr int kStages = 4;
 constexpr int kQPerWarp = 8;       // queries owned by one consumer warp
 constexpr int kMaxLevel = 32;      // constraints beyond this depth are ignored by the pruning bound (still valid)
-constexpr int kSeedPoints = 4096;  // size of the seed neighbourhood (positions) scanned before the traversal bounds are taken
+#ifndef SCHT_SEED_POINTS
+#define SCHT_SEED_POINTS 1024
+#endif
+constexpr int kSeedPoints = SCHT_SEED_POINTS;  // size of the seed neighbourhood (positions) scanned before the traversal bounds are taken
 constexpr int kMaxCuts = 64;       // the traversal of one tile is split into <= 64 subtree jobs (one warp each)
 constexpr int kJobRanges = 8;      // page ranges per (tile, subtree job); overflow coalesces gaps (scans more, stays exact)
 constexpr int kRangeCap = kMaxCuts * kJobRanges;  // range slots per tile
@@ -546,6 +549,62 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
 #pragma unroll 1
         for (int s = 1; s < n_slices; s++) stage_step(s, std::false_type{});
         n_pairs += (unsigned long long)min(kPage, T.n_points - page * kPage);
+
+        // ---- bound bootstrap: while a query's list is not full its bound is +inf and EVERY point of the page would go
+        // through the exact path (that start-up used to dominate the seed scan).  Instead, a bisection on the bit patterns of
+        // the page's 256 fast-path distances finds a value t with at least K valid points at or below it; points beyond
+        // t(1+2^-20) are strictly farther than K others (the fast path is within 2 ulp of the reference arithmetic), so they
+        // cannot be among the K nearest and are dropped without an exact evaluation.  thr[] is warp-uniform.
+        {
+            bool boot = false;
+#pragma unroll
+            for (int qi = 0; qi < kQPerWarp; qi++) boot |= thr[qi] >= 3.0e38f;
+            if (boot && K <= kPage) {
+                uint32_t ok = 0;  // points of this lane that may enter a list (inside the shard; padded ones are +inf anyway)
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int pos = page * kPage + ((e >> 2) ? 128 : 0) + 4 * lane + (e & 3);
+                    if (pos >= P.pos_lo && pos < P.pos_hi) ok |= 1u << e;
+                }
+#pragma unroll
+                for (int qi = 0; qi < kQPerWarp; qi++) {
+                    if (thr[qi] >= 3.0e38f) {
+                        uint32_t v[8];
+#pragma unroll
+                        for (int pp = 0; pp < 4; pp++) {
+                            float lo, hi;
+                            unpack2(acc[qi][pp], lo, hi);
+                            v[2 * pp] = ((ok >> (2 * pp)) & 1u) ? __float_as_uint(lo) : 0x7f800000u;
+                            v[2 * pp + 1] = ((ok >> (2 * pp + 1)) & 1u) ? __float_as_uint(hi) : 0x7f800000u;
+                        }
+                        uint32_t vmin = 0xffffffffu, vmax = 0;
+                        int cnt = 0;
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const bool fin = v[e] < 0x7f7fffffu;  // finite non-negative fast-path distance (NaN patterns are above)
+                            vmin = min(vmin, fin ? v[e] : 0xffffffffu);
+                            vmax = max(vmax, fin ? v[e] : 0u);
+                            cnt += fin ? 1 : 0;
+                        }
+                        cnt = __reduce_add_sync(0xffffffffu, cnt);
+                        if (cnt >= K) {
+                            uint32_t lo = __reduce_min_sync(0xffffffffu, vmin), hi = __reduce_max_sync(0xffffffffu, vmax);
+#pragma unroll 1
+                            for (int iter = 0; iter < 18 && lo < hi; iter++) {
+                                const uint32_t mid = lo + ((hi - lo) >> 1);
+                                int c = 0;
+#pragma unroll
+                                for (int e = 0; e < 8; e++) c += (v[e] <= mid) ? 1 : 0;
+                                c = __reduce_add_sync(0xffffffffu, c);
+                                if (c >= K) hi = mid;       // invariant: at least K valid points are <= hi
+                                else lo = mid + 1;
+                            }
+                            thr[qi] = fminf(__uint_as_float(hi) * 1.000001f, 3.0e38f);
+                        }
+                    }
+                }
+            }
+        }
 
         // ---- candidate filter: anything within the widened K-th distance goes to the exact path ----------
         bool any = false;

@@ -26,6 +26,6 @@ best = 1e9
 for _ in range(3):
     idx, d2, st = ix.query(q, 10, want_stats=True)
     best = min(best, st["ms_main_scan"])
-print("SCHT_EXP", os.environ["SCHT_EXP_ID"], "main_scan_ms", round(best, 3), "exact", st["exact_reevaluations"])
+print("SCHT_EXP", os.environ["SCHT_EXP_ID"], os.environ.get("SCHT_EXP_FLAGS", ""), "main_scan_ms", round(best, 3), "seed_ms", round(st["ms_seed_scan"], 3), "device_ms", round(st["ms_device"], 3), "exact", st["exact_reevaluations"])
 PY
 done
