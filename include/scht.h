@@ -199,6 +199,42 @@ int scht_merge_partial_device(scht_handle* h, const uint64_t* d_keys, int32_t n_
 int scht_handle_info(const scht_handle* h, int32_t* dim, int64_t* n_points, int32_t* n_nodes, int32_t* n_leaves,
                      int32_t* device, int64_t* device_bytes);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-set files.  Replaces read_data / read_data_dim_size / get_dim / get_data
+ * (Code/data_processor.h:5-99: freopen + gets + strtok + atof, one point per line).
+ *   scht_read_text   same file contract: dim = number of `delims`-separated tokens of the first line, one row
+ *                    per line (empty lines included), value = (float)atof(token); mmap'd and parsed on all host
+ *                    cores.  Defined where the reference is not: short lines are zero-filled, extra tokens
+ *                    ignored, a trailing '\r' is a delimiter.  delims NULL/"" = " " (Code/main.cc:146).
+ *   scht_write_text  writes that format ("%.9g", space separated): floats round-trip exactly.
+ *   scht_write_bin / scht_map_bin / scht_unmap_bin
+ *                    flat binary: 32-byte header {"SCHTBIN1", int32 dim, int32 0, int64 n_points, int64 0}
+ *                    followed by n_points*dim little-endian floats, row-major; scht_map_bin returns a
+ *                    read-only mmap view (rows 32-byte aligned), valid until scht_unmap_bin(mapping).
+ *   scht_read_fvecs  the .fvecs format of the SIFT/GIST sets: per row int32 dim, then dim floats.
+ * Matrices returned through float** are malloc'd; release with scht_free.  N*D must stay below 2^32 like in
+ * the reference (Code/Array.hh:1175-1183). */
+int scht_read_text(const char* path, const char* delims, float** data_out, int64_t* n_points, int32_t* dim);
+int scht_write_text(const char* path, const float* data, int64_t n_points, int32_t dim);
+int scht_write_bin(const char* path, const float* data, int64_t n_points, int32_t dim);
+int scht_map_bin(const char* path, const float** data_out, int64_t* n_points, int32_t* dim, void** mapping_out);
+void scht_unmap_bin(void* mapping);
+int scht_read_fvecs(const char* path, float** data_out, int64_t* n_points, int32_t* dim);
+void scht_free(void* p);
+
+/* ------------------------------------------------------------------------------------------------
+ * Experiment-log surface: the text blocks the reference's drivers append to their log
+ * files, line for line -- Convex_Tree<T>::save_tree_info (Code/Convex_Tree.h:964-991) and
+ * GPU_Convex_Tree<T>::save_KNN_running_time_info (Code/GPU_Convex_Tree.h:973-1005; print_ variant :950-971),
+ * numbers formatted like my_strcat / my_strcat_longlong / my_strcat_double (Code/basic_functions.h:313-334).
+ * Counter mapping: (2) quadprog calls = scht_stats.hyperplane_tests, (3) = dist_computations,
+ * (4) = descent_dists, (6) = batch size / scht_stats.batches.
+ * Writes a NUL-terminated string into buf[cap]; *needed (optional) = bytes required incl. the NUL;
+ * buf == NULL with needed != NULL only measures. */
+int scht_format_tree_info(const scht_host_tree* tree, float leaf_pts_percent, char* buf, size_t cap, size_t* needed);
+int scht_format_knn_log(const scht_stats* stats, int64_t n_queries, int32_t K, int64_t batch_size, char* buf, size_t cap,
+                        size_t* needed);
+
 const char* scht_last_error(void);
 int scht_abi_version(void);
 /* Number of visible CUDA devices (0 if none / no driver); never fails. */

@@ -14,6 +14,7 @@
 #include <iostream>
 #include <vector>
 
+#include <string>
 #include "Convex_Tree.h"
 #include "scht.h"
 
@@ -35,10 +36,17 @@ public:
         this->BATCH_SIZE_OF_QUERY_POINTS_PUSCH_TO_DEVICE = batch_size;
         if (dev_ && batch_size > 0) scht_set_batch_size(dev_, batch_size);
     }
-    virtual void print_kNN_running_time_info() {
-        std::cout << "B200: whole kNN " << stats_.ms_total * 1e-3 << " s, device " << stats_.ms_device * 1e-3 << " s, leaf scan "
-                  << stats_.ms_scan * 1e-3 << " s, batches " << stats_.batches << ", dist computations " << stats_.dist_computations
-                  << ", quadprog " << stats_.hyperplane_tests << std::endl;
+    // the reference's log block (Code/GPU_Convex_Tree.h:950-1005), formatted by the library from this call's counters
+    virtual void print_kNN_running_time_info() { std::cout << knn_log_text(); }
+    virtual void save_KNN_running_time_info(FILE* log_file) { write_file_log(knn_log_text().c_str(), log_file); }
+    std::string knn_log_text() const {
+        size_t need = 0;
+        const long long nq = (long long)this->query_points_vec.size();
+        scht_format_knn_log(&stats_, nq, this->K, this->BATCH_SIZE_OF_QUERY_POINTS_PUSCH_TO_DEVICE, nullptr, 0, &need);
+        std::string s(need, '\0');
+        scht_format_knn_log(&stats_, nq, this->K, this->BATCH_SIZE_OF_QUERY_POINTS_PUSCH_TO_DEVICE, &s[0], need, nullptr);
+        s.resize(need ? need - 1 : 0);
+        return s;
     }
     const scht_stats& stats() const { return stats_; }
 

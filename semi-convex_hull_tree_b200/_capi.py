@@ -72,6 +72,15 @@ SYMBOLS = {
     "scht_merge_partial_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scht_handle_info": (C.c_int, [C.c_void_p, i32p, C.POINTER(C.c_int64), i32p, i32p, i32p, C.POINTER(C.c_int64)]),
+    "scht_read_text": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(f32p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "scht_write_text": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
+    "scht_write_bin": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
+    "scht_map_bin": (C.c_int, [C.c_char_p, C.POINTER(f32p), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]),
+    "scht_unmap_bin": (None, [C.c_void_p]),
+    "scht_read_fvecs": (C.c_int, [C.c_char_p, C.POINTER(f32p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "scht_free": (None, [C.c_void_p]),
+    "scht_format_tree_info": (C.c_int, [C.c_void_p, C.c_float, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "scht_format_knn_log": (C.c_int, [C.POINTER(Stats), C.c_int64, C.c_int32, C.c_int64, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "scht_last_error": (C.c_char_p, []),
     "scht_abi_version": (C.c_int, []),
     "scht_device_count": (C.c_int, []),
@@ -270,3 +279,69 @@ class Index:
             self.close()
         except Exception:
             pass
+
+
+# ---- data-set files and log text (include/scht.h "Data-set files", "Experiment-log surface") ----------------------
+def _take_matrix(ptr, n, dim):
+    """copy a malloc'd [n*dim] float matrix into numpy and release it"""
+    out = np.ctypeslib.as_array(ptr, shape=(int(n) * int(dim),)).reshape(int(n), int(dim)).copy()
+    lib().scht_free(ptr)
+    return out
+
+
+def read_text(path, delims=" "):
+    """scht_read_text: the reference's text format (Code/data_processor.h:75-99) -> float32 [n, dim]"""
+    ptr, n, d = f32p(), C.c_int64(), C.c_int32()
+    _check(lib().scht_read_text(os.fsencode(path), delims.encode(), C.byref(ptr), C.byref(n), C.byref(d)))
+    return _take_matrix(ptr, n.value, d.value)
+
+
+def write_text(path, data):
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    _check(lib().scht_write_text(os.fsencode(path), data.ctypes.data, data.shape[0], data.shape[1]))
+
+
+def write_bin(path, data):
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    _check(lib().scht_write_bin(os.fsencode(path), data.ctypes.data, data.shape[0], data.shape[1]))
+
+
+def read_bin(path):
+    """scht_map_bin + copy (the mapping itself is zero-copy; numpy here owns a copy so the file can be unmapped)"""
+    ptr, n, d, m = f32p(), C.c_int64(), C.c_int32(), C.c_void_p()
+    _check(lib().scht_map_bin(os.fsencode(path), C.byref(ptr), C.byref(n), C.byref(d), C.byref(m)))
+    try:
+        if n.value == 0:
+            return np.zeros((0, d.value), dtype=np.float32)
+        return np.ctypeslib.as_array(ptr, shape=(n.value * d.value,)).reshape(n.value, d.value).copy()
+    finally:
+        lib().scht_unmap_bin(m)
+
+
+def read_fvecs(path):
+    ptr, n, d = f32p(), C.c_int64(), C.c_int32()
+    _check(lib().scht_read_fvecs(os.fsencode(path), C.byref(ptr), C.byref(n), C.byref(d)))
+    return _take_matrix(ptr, n.value, d.value)
+
+
+def _format(call):
+    need = C.c_size_t()
+    _check(call(None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _check(call(buf, need.value, None))
+    return buf.value.decode()
+
+
+def format_tree_info(host_tree, leaf_pts_percent):
+    """save_tree_info's text block (Code/Convex_Tree.h:964-991) for a HostTree"""
+    return _format(lambda b, c, n: lib().scht_format_tree_info(host_tree._h, C.c_float(leaf_pts_percent), b, c, n))
+
+
+def format_knn_log(stats, n_queries, K, batch_size):
+    """save_KNN_running_time_info's text block (Code/GPU_Convex_Tree.h:973-1005) from a stats dict or Stats"""
+    st = stats
+    if isinstance(stats, dict):
+        st = Stats()
+        for k, _ in Stats._fields_:
+            setattr(st, k, stats.get(k, 0))
+    return _format(lambda b, c, n: lib().scht_format_knn_log(C.byref(st), n_queries, K, batch_size, b, c, n))

@@ -62,7 +62,7 @@ public:
     // (Code/Convex_Tree.h:518-548, Code/GPU_Convex_Tree.h:150-163).  rand_seed 1 == srand never called.
     B200_Convex_Tree(Matrix<T>& data, float leaf_pts_percent, int alg_type = USE_B200_LEAF_APPRXIMATE_QP, int device = 0,
                      unsigned rand_seed = 1)
-        : ALG_TYPE(alg_type), dim_((int)data.ncols()) {
+        : ALG_TYPE(alg_type), dim_((int)data.ncols()), pct_(leaf_pts_percent) {
         if (leaf_pts_percent <= 0 || leaf_pts_percent >= 0.5f)  // Code/Convex_Tree.h:522-523
             throw std::runtime_error("illegal percent, it should be in (0,0.5)");
         if (scht_build_tree(data.get_matrix_raw_data(), data.nrows(), (int32_t)data.ncols(), leaf_pts_percent, rand_seed, &host_) != SCHT_OK)
@@ -93,33 +93,34 @@ public:
 
     // Code/GPU_Convex_Tree.h:197-204
     void set_batch_size(int batch_size) {
-        if (batch_size > 0) scht_set_batch_size(dev_, batch_size);
+        if (batch_size > 0 && scht_set_batch_size(dev_, batch_size) == SCHT_OK) batch_size_ = batch_size;
     }
 
     int get_nodes_num() const { return scht_host_tree_desc(host_)->n_nodes; }
     int get_leaf_nodes_num() const { return scht_host_tree_desc(host_)->n_leaves; }
     const scht_stats& stats() const { return stats_; }
 
-    // Code/Convex_Tree.h:946-958
-    void print_tree_info() {
-        const scht_tree_desc* d = scht_host_tree_desc(host_);
-        std::cout << "nodes num=" << d->n_nodes << ", leaf nodes num=" << d->n_leaves << ", tree depth=" << d->depth
-                  << ", leaf_pts_num_threshold=" << d->leaf_threshold << ", building tree time=" << scht_host_tree_build_seconds(host_)
-                  << " s\n";
+    // Code/Convex_Tree.h:946-958 / :964-991 -- the reference's text block, formatted by the library (scht_format_tree_info)
+    void print_tree_info() { std::cout << tree_info_text(); }
+    void save_tree_info(FILE* log_file) { write_log(tree_info_text(), log_file); }
+    // Code/GPU_Convex_Tree.h:950-971 / :973-1005 (scht_format_knn_log)
+    void print_kNN_running_time_info() { std::cout << knn_log_text(); }
+    void save_KNN_running_time_info(FILE* log_file) { write_log(knn_log_text(), log_file); }
+    std::string tree_info_text() const {
+        size_t need = 0;
+        scht_format_tree_info(host_, pct_, nullptr, 0, &need);
+        std::string s(need, '\0');
+        scht_format_tree_info(host_, pct_, &s[0], need, nullptr);
+        s.resize(need ? need - 1 : 0);
+        return s;
     }
-    // Code/GPU_Convex_Tree.h:950-971
-    void print_kNN_running_time_info() {
-        std::cout << "whole kNN time=" << stats_.ms_total * 1e-3 << " s, device time=" << stats_.ms_device * 1e-3
-                  << " s, leaf scan time=" << stats_.ms_scan * 1e-3 << " s\n"
-                  << "batch iteration times=" << stats_.batches << ", dist computation times=" << stats_.dist_computations
-                  << ", quadprog times=" << stats_.hyperplane_tests << ", kernel launches=" << stats_.kernel_launches << "\n";
-    }
-    // Code/GPU_Convex_Tree.h:973-1005
-    void save_KNN_running_time_info(FILE* log_file) {
-        if (!log_file) return;
-        fprintf(log_file, "whole kNN time=%f s, device time=%f s, leaf scan time=%f s, batches=%lld, dist computations=%lld, quadprog=%lld\n",
-                stats_.ms_total * 1e-3, stats_.ms_device * 1e-3, stats_.ms_scan * 1e-3, (long long)stats_.batches,
-                (long long)stats_.dist_computations, (long long)stats_.hyperplane_tests);
+    std::string knn_log_text() const {
+        size_t need = 0;
+        scht_format_knn_log(&stats_, n_queries_, K_, batch_size_, nullptr, 0, &need);
+        std::string s(need, '\0');
+        scht_format_knn_log(&stats_, n_queries_, K_, batch_size_, &s[0], need, nullptr);
+        s.resize(need ? need - 1 : 0);
+        return s;
     }
 
     int ALG_TYPE;
@@ -132,6 +133,7 @@ private:
             return;
         }
         K_ = K;
+        n_queries_ = q.nrows();
         size_t n = (size_t)q.nrows() * (size_t)(K > 0 ? K : 0);
         idx_.assign(n, -1);
         dist2_.assign(n, 3.402823466e+38f);
@@ -143,7 +145,18 @@ private:
         if (rc != SCHT_OK) std::cout << "B200_Convex_Tree: " << scht_last_error() << std::endl;
     }
 
+    static void write_log(const std::string& text, FILE* fp) {  // write_file_log, Code/basic_functions.h:338-348
+        if (!fp) {
+            std::cout << "can't open file\n";
+            return;
+        }
+        fseek(fp, 0, SEEK_END);
+        fwrite(text.data(), text.size(), 1, fp);
+    }
+
     int dim_, K_ = 0;
+    float pct_;
+    long long n_queries_ = 0, batch_size_ = 1000000;  // default batch: Code/main.cc:670
     scht_host_tree* host_ = nullptr;
     scht_handle* dev_ = nullptr;
     scht_stats stats_{};
