@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscht_b200.so")
+LIB_PATH = os.environ.get("SCHT_LIB") or os.path.join(_HERE, "libscht_b200.so")  # SCHT_LIB: A/B experiments only
 SCHT_MAX_K = 128
 
 STATUS = {0: "SCHT_OK", -1: "SCHT_ERR_INVALID_ARG", -2: "SCHT_ERR_DIM_MISMATCH", -3: "SCHT_ERR_NO_DEVICE",

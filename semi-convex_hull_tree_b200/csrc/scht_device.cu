@@ -58,6 +58,7 @@ struct scht_handle {
     int device = 0;
     int sm_count = 0;
     int max_smem = 0;
+    int n_sm = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     DevTree T{};
@@ -68,6 +69,7 @@ struct scht_handle {
     int scan_variant = 2;
     int traverse_sampling = 1;    // sample the traversal before running it for every tile (SCHT_TRAVERSE_SAMPLING=0 disables)
     int tc_mode = 2;              // tensor-core prefilter: 0 off, 1 always, 2 auto (per batch, from the seed bounds)
+    int tc_split = 1;             // page segments per prefilter tile: 0 never split, 1 auto, n > 1 forced (SCHT_TC_SPLIT)
     int kp = 0;                   // padded K of the tensor-core page image (0: not built)
     const unsigned char* tcpages = nullptr;
     float tc_scale = 1.f, pabs_sum = 0.f, norm_unit = 1.f;
@@ -76,7 +78,7 @@ struct scht_handle {
     float pnorm_max = 0.f;
     int64_t tc_batches = 0;
     std::vector<int> h_leaf_start, h_leaf_count;
-    DevBuf q, q_leaf, hist, q_order, state, ranges, n_ranges, idx, d2, dist, counters;
+    DevBuf q, q_leaf, hist, q_order, state, ranges, n_ranges, idx, d2, dist, counters, seg_keys;
 };
 
 namespace {
@@ -331,10 +333,42 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             TC.trace = d_trace;
             if (const char* ev = getenv("SCHT_TC_DEBUG")) TC.debug = atoi(ev);
 #endif
+            // Tail effect: n_tiles CTAs of equal length on n_sm SMs take ceil(n_tiles/n_sm) rounds (782 tiles on 148 SMs: 6 rounds
+            // for 5.28 rounds of work).  Splitting every tile's page list into S segments (own CTA each, partial lists merged by
+            // k_merge_partial) makes the rounds S times shorter: pick the S <= 8 with the smallest ceil(S*n_tiles/n_sm)/S, charging
+            // 5 % per extra segment for the repeated set-up and the looser early bounds (measured).  Also what keeps a SMALL batch from
+            // running on a handful of SMs.
+            int n_seg = 1;
+            if (!partial && h->tc_split) {
+                const int page_lo = P.pos_lo / kPage, page_hi = (P.pos_hi + kPage - 1) / kPage;
+                double best = 1e30;
+                for (int S = 1; S <= 8; S++) {
+                    if (S > 1 && (page_hi - page_lo) / S < 64) break;
+                    const double rounds = std::ceil((double)S * n_tiles_main / h->n_sm) / S * (1.0 + 0.05 * (S - 1));
+                    if (rounds < best - 1e-9) {
+                        best = rounds;
+                        n_seg = S;
+                    }
+                }
+                if (h->tc_split > 1) n_seg = std::min(8, h->tc_split);  // SCHT_TC_SPLIT=n forces n segments
+                if (n_seg > 1) {
+                    CU_TRY(h->seg_keys.reserve((size_t)n_seg * nq * K * sizeof(uint64_t)));
+                    TC.S.keys_out = h->seg_keys.as<uint64_t>();
+                    TC.n_seg = n_seg;
+                    TC.seg_page0 = page_lo;
+                    TC.seg_pages = (page_hi - page_lo + n_seg - 1) / n_seg;
+                }
+            }
+            if (n_seg == 1) TC.n_seg = 1;
             size_t smem = tc_smem_bytes(T.dpad, h->kp, K, tc_stages);
             CU_TRY(cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_scan_tc<<<n_tiles_main, kTcThreads, smem, s>>>(TC);
+            k_scan_tc<<<n_tiles_main * n_seg, kTcThreads, smem, s>>>(TC);
             CU_TRY(cudaGetLastError());
+            if (n_seg > 1) {
+                k_merge_partial<<<(nq + 127) / 128, 128, 0, s>>>(T, h->seg_keys.as<uint64_t>(), n_seg, nq, K, P.idx_out, P.d2_out, P.dist_out);
+                CU_TRY(cudaGetLastError());
+                launches++;
+            }
             h->tc_batches++;
 #ifdef SCHT_TC_PROF
             {
@@ -502,6 +536,7 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    h->n_sm = std::max(1, prop.multiProcessorCount);
     h->depth = depth;
     h->h_leaf_start.assign(t->leaf_start, t->leaf_start + L);
     h->h_leaf_count.assign(t->leaf_count, t->leaf_count + L);
@@ -632,6 +667,7 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     // tensor-core page image (centred, TF32-rounded coordinates + |p'|^2 hi/lo), see scht_tc.cuh
     if (const char* ev = getenv("SCHT_TRAVERSE_SAMPLING")) h->traverse_sampling = atoi(ev) != 0;
     if (const char* ev = getenv("SCHT_TC")) h->tc_mode = std::max(0, std::min(2, atoi(ev)));
+    if (const char* ev = getenv("SCHT_TC_SPLIT")) h->tc_split = std::max(0, atoi(ev));
     {
         const int kp = (dim + 3 + 15) & ~15;
         const size_t tbytes = (size_t)T.n_pages * tc_page_bytes(kp);
@@ -697,7 +733,7 @@ extern "C" void scht_destroy(scht_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->owned) cudaFree(p);
-    for (DevBuf* b : {&h->q, &h->q_leaf, &h->hist, &h->q_order, &h->state, &h->ranges, &h->n_ranges, &h->idx, &h->d2, &h->dist, &h->counters})
+    for (DevBuf* b : {&h->q, &h->q_leaf, &h->hist, &h->q_order, &h->state, &h->ranges, &h->n_ranges, &h->idx, &h->d2, &h->dist, &h->counters, &h->seg_keys})
         b->release();
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);

@@ -341,8 +341,9 @@ struct PageWalk {
     const int2* seed;
     int n_seed;  // 0: nothing to skip
     int g, r, cnt_g, page, cur_end, sr;  // pages [page, cur_end) of the current range are still to be returned
-    __device__ PageWalk(const int2* l, const int* c, int ng, int st, const int2* s, int ns)
-        : list(l), cnt(c), n_groups(ng), stride(st), seed(s), n_seed(ns), g(0), r(0), page(0), cur_end(0), sr(0) {
+    int w_lo, w_hi;                      // only pages inside the window [w_lo, w_hi) are returned (page segments of a split tile)
+    __device__ PageWalk(const int2* l, const int* c, int ng, int st, const int2* s, int ns, int win_lo = 0, int win_hi = 0x7fffffff)
+        : list(l), cnt(c), n_groups(ng), stride(st), seed(s), n_seed(ns), g(0), r(0), page(win_lo), cur_end(0), sr(0), w_lo(win_lo), w_hi(win_hi) {
         cnt_g = (ng > 0) ? c[0] : 0;
     }
     __device__ __forceinline__ bool next(int& out) {
@@ -367,7 +368,7 @@ struct PageWalk {
             const int2 rg = list[(size_t)g * stride + r];
             r++;
             if (rg.x > page) page = rg.x;
-            cur_end = rg.y;
+            cur_end = min(rg.y, w_hi);
         }
     }
 };
@@ -1009,7 +1010,9 @@ __global__ void k_merge_partial(DevTree T, const uint64_t* __restrict__ keys, in
         int idx = -1;
         float d2 = 3.402823466e+38f;
         if (bl >= 0) {
-            head[bl]++;
+            // a key identifies a point: lists that started from the same state (page segments of one tile) hold duplicates
+            for (int l = 0; l < n_lists; l++)
+                if (head[l] < K && keys[((size_t)l * nq + i) * K + head[l]] == best) head[l]++;
             if (best != kEmptyKey) {
                 idx = T.orig_idx[(uint32_t)best & 0x7fffffffu];
                 d2 = __uint_as_float((uint32_t)(best >> 32));

@@ -53,6 +53,9 @@ struct TcScanParams {
     float norm_unit;         // power of two u: the norm slots hold s^2|p'|^2 / u, the query operand holds u
     int kp;                  // padded K (multiple of 16) = ceil16(dim + 3)
     int n_stages;            // slice stages in shared memory (3..kTcMaxStages)
+    int n_seg;               // page segments per tile (>= 1): CTA b scans segment b / n_tiles of tile b % n_tiles and, when
+    int seg_pages;           //   n_seg > 1, writes its key lists to S.keys_out[segment][query][K] (merged by k_merge_partial);
+    int seg_page0;           //   segment s = pages [seg_page0 + s*seg_pages, +seg_pages)
     int debug;               // SCHT_TC_PROF builds only: 1 = no pair passes the filter, 2 = also skip the min tree
     long long* trace;        // SCHT_TC_PROF builds: [64 pages][8] clock64 stamps of tile 0 (pages 2000..2063)
 };
@@ -220,7 +223,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tq_s + kTcQ);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
+    const int n_tiles = (P.nq + kTcQ - 1) / kTcQ;
+    const int seg = (TP.n_seg > 1) ? (int)blockIdx.x / n_tiles : 0;  // segment-major: CTAs that run together scan the same pages (L2)
+    const int tile = (int)blockIdx.x - seg * n_tiles;
     const int q_begin = tile * kTcQ;
     const int nq_tile = min(kTcQ, P.nq - q_begin);
     const float scale = TP.scale;
@@ -283,7 +288,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
 
     // No seed-page exclusion here: the seed scan ran on 32-query tiles, so a page may have been seed-scanned for some of
     // these 128 queries only.  Re-scanning is cheap in this kernel and list insertion is idempotent.
-    PageWalk walk(P.ranges + (size_t)tile * kRangeCap, P.n_ranges + (size_t)tile * kMaxCuts, T.n_cuts, kJobRanges, nullptr, 0);
+    const int w_lo = (TP.n_seg > 1) ? TP.seg_page0 + seg * TP.seg_pages : 0;
+    const int w_hi = (TP.n_seg > 1) ? ((seg == TP.n_seg - 1) ? 0x7fffffff : w_lo + TP.seg_pages) : 0x7fffffff;
+    PageWalk walk(P.ranges + (size_t)tile * kRangeCap, P.n_ranges + (size_t)tile * kMaxCuts, T.n_cuts, kJobRanges, nullptr, 0, w_lo, w_hi);
     const int n_slices = (kp + kTcKSlice - 1) / kTcKSlice;
     int page;
 
@@ -480,7 +487,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                 if (ql >= nq_tile) break;
                 const uint64_t* L = lists + (size_t)ql * K;
                 const int qid = qids[ql];
-                if (P.write_mode == kWriteFinal) {
+                if (TP.n_seg > 1) {  // a page segment of a split tile: partial lists, merged afterwards
+                    uint64_t* dst = P.keys_out + ((size_t)seg * P.nq + qid) * K;
+                    for (int k = lane; k < K; k += 32) dst[k] = L[k];
+                } else if (P.write_mode == kWriteFinal) {
                     for (int k = lane; k < K; k += 32) {
                         uint64_t key = L[k];
                         int idx = -1;
