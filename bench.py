@@ -38,6 +38,7 @@ WORKLOADS = {
     "siftlike_1Mx128_q100k_K10": (1_000_000, 128, 100_000, 10, 0.0005, "sift"),
     "posture_like_78095x15_self_K10": (78_095, 15, 78_095, 10, 0.005, "posture"),
     "smoke_50kx16_q4k_K10": (50_000, 16, 4_096, 10, 0.005, "uniform"),
+    "uniform_100Mx16_q100k_K10": (100_000_000, 16, 100_000, 10, 0.000005, "uniform"),  # cfg5's data set on one GPU (13 GB device image)
 }
 
 
@@ -196,13 +197,14 @@ def main():
     data, queries = make_data(kind, n, dim, nq, 1234)
     if world > 1:  # weak scaling: every rank gets its own 100k queries, the tree is replicated
         _, queries = make_data(kind, 1, dim, nq, 1234 + 17 * rank) if kind == "uniform" else (None, queries[np.random.default_rng(rank).permutation(nq)])
+    # the tree: built on this rank's GPU by scht_build_tree_device (bit-identical to the host builder, tests/test_gpu_build.py)
     t0 = time.perf_counter()
-    ht = pkg.HostTree(data, pct, 1)
+    ht = pkg.HostTree(data, pct, 1, device=local_rank)
     t_build = time.perf_counter() - t0
     ix = pkg.Index(ht, device=local_rank)
     info = ix.info()
     arr = ht.arrays()
-    config.update({"n_leaves": int(arr["n_leaves"]), "tree_depth": int(arr["depth"]), "host_build_s": round(t_build, 2),
+    config.update({"n_leaves": int(arr["n_leaves"]), "tree_depth": int(arr["depth"]), "device_build_s": round(t_build, 2),
                    "device_tree_MB": info["device_bytes"] >> 20})
 
     # device-resident leg
@@ -272,6 +274,8 @@ def main():
 
     # CPU baseline + the reference algorithm's scan volume (algorithmic bytes of the roofline)
     s_ref = None
+    if n > 10_000_000:
+        args.no_cpu_baseline = True  # the reference's single-threaded host build alone would take hours at this size
     if not args.no_cpu_baseline:
         try:
             guess_qps_core = 30.0 * (1_000_000 * 16) / (n * dim)
@@ -299,7 +303,15 @@ def main():
     achieved = alg_bytes / main_s / 1e9
     clk = (line["clocks"].get("sm_mhz") or 1965) * 1e6
     pairs = stats["dist_computations"]
-    line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(args.workload, {}).get("k_scan_tc" if used_tc else "k_scan")
+        if ent:
+            traffic = ent["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
                         "kernel": "k_scan_tc (main scan, tensor-core prefilter + exact rescoring)" if used_tc else "k_scan (main scan)",
                         "kernel_ms": stats["ms_main_scan"], "launches_per_step": 1,
@@ -315,8 +327,8 @@ def main():
                                       "achieved_tflops_issued": pairs * kp * 2 / main_s / 1e12, "peak_tflops": tpeak,
                                       "frac_issued": pairs * kp * 2 / main_s / 1e12 / tpeak,
                                       "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; FP16 and BF16 MMA run at the same rate)",
-                                      "note": "the MMA is 1/8 of the kernel time; the epilogue (one TMEM read + min per pair) and the "
-                                              "MMA->epilogue hand-off latency bound the kernel, not the tensor pipe"}
+                                      "note": "tensor pipe ~30 % busy (ncu): the epilogue (one TMEM read + one min per pair, ALU pipe ~60 % "
+                                              "busy) and the MMA->epilogue hand-off latency bound the kernel, not the tensor pipe"}
     else:
         line["roofline"]["fp32"] = {"lane_ops_per_s": pairs * dim * 2 / main_s,
                                     "frac_of_128_lanes_per_clk_per_sm": pairs * dim * 2 / main_s / (148 * 128 * clk)}

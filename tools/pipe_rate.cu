@@ -92,8 +92,8 @@ __device__ __forceinline__ float tree(const uint32_t (&v)[32]) {
 
 constexpr int kStages = 6;
 
-template <int NBUF, int GROUPS, int SPLIT, int ISS, int PROD, int TREE, int SPIN, int KP>
-__global__ void __launch_bounds__((GROUPS * 4 + ISS + PROD) * 32, 1) k(const unsigned char* __restrict__ pages, int n_pages, int iters, float thr,
+template <int NBUF, int GROUPS, int SPLIT, int ISS, int PROD, int TREE, int SPIN, int KP, int FEAT>
+__global__ void __launch_bounds__((GROUPS * 4 + ISS + PROD + ((FEAT & 2) ? 4 : 0)) * 32, 1) k(const unsigned char* __restrict__ pages, int n_pages, int iters, float thr,
                                                                       float* out, unsigned long long* cycles) {
     constexpr int N = 512 / NBUF;          // columns per buffer fill (= MMA N)
     constexpr int UPP = 256 / N;           // buffer fills (units) per page
@@ -105,7 +105,13 @@ __global__ void __launch_bounds__((GROUPS * 4 + ISS + PROD) * 32, 1) k(const uns
     __half* sA = reinterpret_cast<__half*>(smem + kStages * KP * 512);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 128 * KP);   // full[6], empty[6], tfull[NBUF], tempty[NBUF]
     __shared__ uint32_t slot;
+    __shared__ float tq_s[128];
+    __shared__ unsigned int ring_resv[4], ring_head[4], done_flag[16];
+    __shared__ unsigned long long ring[4][256];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 128) tq_s[tid] = thr;
+    if (tid < 4) { ring_resv[tid] = 0; ring_head[tid] = 0; }
+    if (tid < 16) done_flag[tid] = 0;
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages, tfull0 = empty0 + 8 * kStages, tempty0 = tfull0 + 8 * NBUF;
     for (int i = tid; i < 128 * KP; i += blockDim.x) sA[i] = __float2half(0.001f * (i % 97));
     if (tid == 0) {
@@ -162,9 +168,54 @@ __global__ void __launch_bounds__((GROUPS * 4 + ISS + PROD) * 32, 1) k(const uns
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         if (lane == 0) arrive(tempty0 + 8 * buf);
                     }
-                    float m = fminf(tree<TREE>(va), tree<TREE>(vb));
-                    if (m <= thr) acc += m;
+                    if (FEAT & 1) {
+                        // like the product kernel: per-query bound re-read from shared memory, one vote + branch per 32 columns,
+                        // survivors reserved with a shared-memory atomic
+                        const float tq = *reinterpret_cast<volatile float*>(&tq_s[quad * 32 + lane]);
+                        const float ma = tree<TREE>(va);
+                        bool hit = ma <= tq;
+                        if (FEAT & 4) hit |= ((u * 2654435761u + warp * 40503u + lane * 97u + c) & 0x3fff) < 9;  // ~5 % of the warp calls
+                        if (__any_sync(0xffffffffu, hit)) {
+                            if (hit) {
+                                unsigned int sl = atomicAdd(&ring_resv[quad], 1u);
+                                reinterpret_cast<volatile unsigned long long*>(ring[quad])[sl & 255] = ((unsigned long long)lane << 32) | u;
+                            }
+                            __syncwarp();
+                        }
+                        const float mb = tree<TREE>(vb);
+                        hit = mb <= tq;
+                        if (FEAT & 4) hit |= ((u * 2246822519u + warp * 40503u + lane * 97u + c) & 0x3fff) < 9;
+                        if (__any_sync(0xffffffffu, hit)) {
+                            if (hit) {
+                                unsigned int sl = atomicAdd(&ring_resv[quad], 1u);
+                                reinterpret_cast<volatile unsigned long long*>(ring[quad])[sl & 255] = ((unsigned long long)lane << 32) | u;
+                            }
+                            __syncwarp();
+                        }
+                    } else {
+                        float m = fminf(tree<TREE>(va), tree<TREE>(vb));
+                        if (m <= thr) acc += m;
+                    }
                 }
+            }
+        }
+        if (lane == 0) *reinterpret_cast<volatile unsigned int*>(&done_flag[warp]) = 1;
+    } else if (warp >= GROUPS * 4 + ISS + PROD) {
+        // ---- rescorer stand-ins: poll the quadrant's ring counter like the product's rescorers ----
+        const int quad = warp - (GROUPS * 4 + ISS + PROD);
+        unsigned int head = 0;
+        for (;;) {
+            bool fin = true;
+            for (int g = 0; g < GROUPS; g++) fin = fin && (*reinterpret_cast<volatile unsigned int*>(&done_flag[quad + 4 * g]) != 0);
+            const unsigned int r = *reinterpret_cast<volatile unsigned int*>(&ring_resv[quad]);
+            if (r != head) {
+                unsigned long long e = reinterpret_cast<volatile unsigned long long*>(ring[quad])[(head + lane) & 255];
+                acc += (float)(e & 0xff);
+                head = r;
+                *reinterpret_cast<volatile unsigned int*>(&ring_head[quad]) = head;
+            } else {
+                if (fin) break;
+                __nanosleep(4000);
             }
         }
     } else if (warp < GROUPS * 4 + ISS) {
@@ -190,7 +241,7 @@ __global__ void __launch_bounds__((GROUPS * 4 + ISS + PROD) * 32, 1) k(const uns
             }
             __syncwarp();
         }
-    } else {
+    } else if (warp < GROUPS * 4 + ISS + PROD) {
         // ---- producers: page p handled by producer p % PROD ----
         const int me = warp - GROUPS * 4 - ISS;
         for (int pg = me; pg < iters; pg += PROD) {
@@ -213,20 +264,20 @@ __global__ void __launch_bounds__((GROUPS * 4 + ISS + PROD) * 32, 1) k(const uns
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-template <int NBUF, int GROUPS, int SPLIT, int ISS, int PROD, int TREE, int SPIN, int KP>
+template <int NBUF, int GROUPS, int SPLIT, int ISS, int PROD, int TREE, int SPIN, int KP, int FEAT = 0>
 void run(int sms, const unsigned char* pages, int n_pages, float* out, unsigned long long* cyc) {
     const int iters = 6000;
-    auto kern = k<NBUF, GROUPS, SPLIT, ISS, PROD, TREE, SPIN, KP>;
+    auto kern = k<NBUF, GROUPS, SPLIT, ISS, PROD, TREE, SPIN, KP, FEAT>;
     size_t smem = (size_t)kStages * KP * 512 + 128 * KP * 2 + 512;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int threads = (GROUPS * 4 + ISS + PROD) * 32;
+    const int threads = (GROUPS * 4 + ISS + PROD + ((FEAT & 2) ? 4 : 0)) * 32;
     kern<<<sms, threads, smem>>>(pages, n_pages, 50, -1.f, out, cyc);
     cudaMemset(cyc, 0, 8);
     kern<<<sms, threads, smem>>>(pages, n_pages, iters, -1.f, out, cyc);
     cudaError_t e = cudaDeviceSynchronize();
     unsigned long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
-    printf("NBUF=%d N=%3d groups=%d split=%d teams=%d iss=%d prod=%d tree=%d spin=%d K'=%d : %7.1f cycles/page  %s\n", NBUF, 512 / NBUF, GROUPS, SPLIT,
-           GROUPS / SPLIT, ISS, PROD, TREE, SPIN, KP, (double)c / sms / iters, cudaGetErrorString(e));
+    printf("NBUF=%d N=%3d groups=%d split=%d teams=%d iss=%d prod=%d tree=%d spin=%d K'=%d feat=%d : %7.1f cycles/page  %s\n", NBUF, 512 / NBUF, GROUPS, SPLIT,
+           GROUPS / SPLIT, ISS, PROD, TREE, SPIN, KP, FEAT, (double)c / sms / iters, cudaGetErrorString(e));
     fflush(stdout);
 }
 
@@ -258,6 +309,18 @@ int main(int argc, char** argv) {
         run<4, 2, 1, 4, 2, 2, 0, 32>(sms, pages, n_pages, out, cyc);
         run<8, 4, 1, 4, 2, 0, 0, 32>(sms, pages, n_pages, out, cyc);   // 8 buffers of 64 columns
         run<8, 4, 1, 4, 2, 2, 0, 32>(sms, pages, n_pages, out, cyc);
+    }
+    if (set == 1) {
+        // the product kernel's structure (4 buffers of 128 columns, 2 teams x 2 column halves, 4 issuers, 1 producer) with the
+        // product's extra features switched on one by one: 1 = per-query bound from smem + vote + branch (+ atomic push code),
+        // 2 = four polling rescorer warps, 4 = ~5 % of the warp calls really push
+        run<4, 4, 2, 4, 1, 2, 0, 32, 0>(sms, pages, n_pages, out, cyc);
+        run<4, 4, 2, 4, 1, 2, 0, 32, 1>(sms, pages, n_pages, out, cyc);
+        run<4, 4, 2, 4, 1, 2, 0, 32, 2>(sms, pages, n_pages, out, cyc);
+        run<4, 4, 2, 4, 1, 2, 0, 32, 3>(sms, pages, n_pages, out, cyc);
+        run<4, 4, 2, 4, 1, 2, 0, 32, 7>(sms, pages, n_pages, out, cyc);
+        run<4, 4, 2, 4, 1, 1, 0, 32, 7>(sms, pages, n_pages, out, cyc);
+        run<4, 4, 2, 4, 1, 0, 0, 32, 7>(sms, pages, n_pages, out, cyc);
     }
     return 0;
 }
