@@ -99,6 +99,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity), "r"(kMbarSuspendNs)
         : "memory");
 }
+#ifndef SCHT_PRODUCER_SLEEP_NS
+#define SCHT_PRODUCER_SLEEP_NS 200
+#endif
 // Producer-side wait: the producer lane is normally several stages ahead, so it polls with a sleep in between instead
 // of spinning (a spinning lane steals issue slots from the consumer warps that share its scheduler).
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
@@ -114,7 +117,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(200);
+        __nanosleep(SCHT_PRODUCER_SLEEP_NS);
     }
 }
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion counted on an mbarrier.
@@ -499,6 +502,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
         thr[qi] = (qw0 + qi < nq_tile) ? fminf(kth * 1.000001f, 3.402823466e+38f) : -1.f;
     }
     const bool brute = (P.mode == kScanAll);
+    // Narrow points (the whole page is ONE stage): the stage is handed back to the producer only after the page's exact
+    // path, which then reads its candidates' coordinates from shared memory instead of L2 (a ~700-cycle round trip per
+    // batch of 8 loads, most of the seed scan's time).
+    const bool hold_stage = (n_slices == 1);
     unsigned long long n_pairs = 0;
     unsigned int n_exact = 0, n_ins = 0;
 
@@ -543,9 +550,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
                 for (int row = 1; row < rows; row++) row_step(sp + row * kPage, qp + row * TQ, std::false_type{});
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[st]);
+            if (!hold_stage && lane == 0) mbar_arrive(&empty_bar[st]);
             it++;
         };
+        const int held_st = it % kStages;  // (only meaningful when hold_stage)
         stage_step(0, std::true_type{});
 #pragma unroll 1
         for (int s = 1; s < n_slices; s++) stage_step(s, std::false_type{});
@@ -648,7 +656,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
                             bits &= bits - 1;
                             int in_page = ((e >> 2) ? 128 : 0) + 4 * lane + (e & 3);
                             pos = page * kPage + in_page;
-                            const float* pg = T.pages + (size_t)page * dpad * kPage + in_page;
+                            const float* pg = hold_stage ? stage_mem + (size_t)held_st * kRowsPerStage * kPage + in_page
+                                                         : T.pages + (size_t)page * dpad * kPage + in_page;
                             const float* qq = qs + qw0 + qi;
                             // loads first (8 dims in flight), then the sequential reference chain: the chain would otherwise
                             // serialise one L2 round trip per dimension
@@ -685,6 +694,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
             }
 #pragma unroll
             for (int qi = 0; qi < kQPerWarp; qi++) thr[qi] = new_thr[qi];
+        }
+        if (hold_stage) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[held_st]);
         }
     }
 

@@ -8,7 +8,7 @@ for e in ${SCHT_EXP_LIST:-0 1 3 5}; do
   mkdir -p tools/bin/exp$e
   NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -DSCHT_EXP=$e $SCHT_EXP_FLAGS"
   $NV -c -o tools/bin/exp$e/scht_device.o $C/scht_device.cu
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tools/bin/libscht_exp$e.so tools/bin/exp$e/scht_device.o $C/build/scht_build.o $C/build/tree_builder.o $C/build/scht_error.o -cudart shared
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tools/bin/libscht_exp$e.so tools/bin/exp$e/scht_device.o $C/build/scht_build.o $C/build/tree_builder.o $C/build/scht_error.o $C/build/scht_io.o -cudart shared
 done
 for e in ${SCHT_EXP_LIST:-0 1 3 5}; do
 SCHT_EXP_ID=$e timeout 90 python - 2>&1 <<'PY'
