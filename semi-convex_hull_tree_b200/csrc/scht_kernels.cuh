@@ -349,6 +349,27 @@ struct PageWalk {
         : list(l), cnt(c), n_groups(ng), stride(st), seed(s), n_seed(ns), g(0), r(0), page(win_lo), cur_end(0), sr(0), w_lo(win_lo), w_hi(win_hi) {
         cnt_g = (ng > 0) ? c[0] : 0;
     }
+    // Next run of consecutive pages [lo, hi) (no seed ranges to skip): the caller's inner loop is a plain counter, which
+    // matters for the single-warp roles of k_scan_tc whose per-page instruction count sits on the critical path.
+    __device__ __forceinline__ bool next_range(int& lo, int& hi) {
+        for (;;) {
+            while (g < n_groups && r >= cnt_g) {
+                g++;
+                r = 0;
+                if (g < n_groups) cnt_g = cnt[g];
+            }
+            if (g >= n_groups) return false;
+            const int2 rg = list[(size_t)g * stride + r];
+            r++;
+            const int x = max(rg.x, page), y = min(rg.y, w_hi);
+            if (x < y) {
+                lo = x;
+                hi = y;
+                page = y;
+                return true;
+            }
+        }
+    }
     __device__ __forceinline__ bool next(int& out) {
         for (;;) {
             if (page < cur_end) {  // fast path: registers only (the range list lives in global memory)

@@ -292,14 +292,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     const int w_hi = (TP.n_seg > 1) ? ((seg == TP.n_seg - 1) ? 0x7fffffff : w_lo + TP.seg_pages) : 0x7fffffff;
     PageWalk walk(P.ranges + (size_t)tile * kRangeCap, P.n_ranges + (size_t)tile * kMaxCuts, T.n_cuts, kJobRanges, nullptr, 0, w_lo, w_hi);
     const int n_slices = (kp + kTcKSlice - 1) / kTcKSlice;
-    int page;
+    int page, run_lo, run_hi;
 
     if (warp == kTcEpiWarps) {
         // ================= producer: the whole warp walks, one elected lane issues the bulk copies =================
         {
             uint32_t st = 0, ph = 0, ppg = 0;  // stage ring position, kept incrementally (a division per page would sit on this warp's critical path)
             const size_t page_bytes = tc_page_bytes(kp);
-            while (walk.next(page)) {
+            while (walk.next_range(run_lo, run_hi)) for (page = run_lo; page < run_hi; page++) {
                 const unsigned char* src = TP.tcpages + (size_t)page * page_bytes;
                 for (int s = 0; s < n_slices; s++) {
                     mbar_wait(&empty_b[st], ph ^ 1);
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                 ph ^= 1;
             }
         };
-        while (walk.next(page)) {
+        while (walk.next_range(run_lo, run_hi)) for (page = run_lo; page < run_hi; page++) {
             if ((int)(pg & 1) != my_par) {  // the other parity's issuer handles this page
                 advance((uint32_t)n_slices);
                 pg++;
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
             };
 
             uint32_t pg = 0;
-            while (walk.next(page)) {
+            while (walk.next_range(run_lo, run_hi)) for (page = run_lo; page < run_hi; page++) {
                 const uint32_t buf = 2 * (pg & 1) + half;
                 mbar_wait(&tfull_b[buf], (pg >> 1) & 1);
                 TC_STAMP(warp == 0, pg, 5);
