@@ -70,6 +70,7 @@ struct scht_handle {
     int traverse_sampling = 1;    // sample the traversal before running it for every tile (SCHT_TRAVERSE_SAMPLING=0 disables)
     int tc_mode = 2;              // tensor-core prefilter: 0 off, 1 always, 2 auto (per batch, from the seed bounds)
     int tc_split = 1;             // page segments per prefilter tile: 0 never split, 1 auto, n > 1 forced (SCHT_TC_SPLIT)
+    int tc_issuers = 0;           // MMA issuer warps of k_scan_tc: 0 auto (2 for one K slice per page, else 4), or 2 / 4 (SCHT_TC_ISSUERS)
     int kp = 0;                   // padded K of the tensor-core page image (0: not built)
     const unsigned char* tcpages = nullptr;
     float tc_scale = 1.f, pabs_sum = 0.f, norm_unit = 1.f;
@@ -361,8 +362,15 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             }
             if (n_seg == 1) TC.n_seg = 1;
             size_t smem = tc_smem_bytes(T.dpad, h->kp, K, tc_stages);
-            CU_TRY(cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_scan_tc<<<n_tiles_main * n_seg, kTcThreads, smem, s>>>(TC);
+            int n_iss = (h->kp <= kTcKSlice) ? 2 : 4;  // one K slice per page: two issuers (+3 %); several: four (+7 %)
+            if (h->tc_issuers == 2 || h->tc_issuers == 4) n_iss = h->tc_issuers;  // SCHT_TC_ISSUERS
+            if (n_iss == 2) {
+                CU_TRY(cudaFuncSetAttribute(k_scan_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_scan_tc<2><<<n_tiles_main * n_seg, tc_threads(2), smem, s>>>(TC);
+            } else {
+                CU_TRY(cudaFuncSetAttribute(k_scan_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_scan_tc<4><<<n_tiles_main * n_seg, tc_threads(4), smem, s>>>(TC);
+            }
             CU_TRY(cudaGetLastError());
             if (n_seg > 1) {
                 k_merge_partial<<<(nq + 127) / 128, 128, 0, s>>>(T, h->seg_keys.as<uint64_t>(), n_seg, nq, K, P.idx_out, P.d2_out, P.dist_out);
@@ -668,6 +676,7 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     if (const char* ev = getenv("SCHT_TRAVERSE_SAMPLING")) h->traverse_sampling = atoi(ev) != 0;
     if (const char* ev = getenv("SCHT_TC")) h->tc_mode = std::max(0, std::min(2, atoi(ev)));
     if (const char* ev = getenv("SCHT_TC_SPLIT")) h->tc_split = std::max(0, atoi(ev));
+    if (const char* ev = getenv("SCHT_TC_ISSUERS")) h->tc_issuers = atoi(ev);
     {
         const int kp = (dim + 3 + 15) & ~15;
         const size_t tbytes = (size_t)T.n_pages * tc_page_bytes(kp);

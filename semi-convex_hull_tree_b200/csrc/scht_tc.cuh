@@ -13,15 +13,15 @@
 // before it may enter the query's top-K list, so results stay bit-identical; the tensor core only decides which of
 // the ~10^11 pairs are worth an exact evaluation (about 3 in 10^4).
 //
-// Roles: warps 0-15 epilogue, warp 16 = producer lane (cp.async.bulk of page slices already stored in the UMMA
-// K-major no-swizzle layout), warps 17-20 = MMA issuers, one per TMEM buffer.  The unit of the MMA->epilogue pipeline
-// is a HALF page (128 points, N=128): the 512 TMEM columns hold four 128-column accumulator buffers; half page g of
-// page p lives in buffer 2(p&1)+g.  Epilogue warps 8g..8g+7 process the half pages g: warp w reads TMEM lanes
-// 32(w%4)..+31 (thread = query) and 64 of the buffer's 128 columns; survivors go into the warp's ring.  Four
-// independent issue streams and two double-buffered epilogue groups hide the hand-off latencies (mbarrier waits, MMA
-// issue, commits: ~900 cycles per page for a single issuer).  Warps 21-24 are the RESCORERS: rescorer r consumes the rings of the four epilogue warps of lane quadrant r, re-evaluates the survivors
-// exactly, owns the quadrant's 32 top-K lists (no locks) and publishes the tightened bounds, so the MMA->epilogue
-// pipeline never waits for an exact evaluation.
+// Roles (23 or 25 warps): warps 0-15 epilogue, warp 16 = producer lane (cp.async.bulk of page slices already
+// stored in the UMMA K-major no-swizzle layout), then 2 or 4 MMA issuer warps (one per page parity or per buffer).  The unit of the
+// MMA->epilogue pipeline is a HALF page (128 points, N=128): the 512 TMEM columns hold four 128-column accumulator
+// buffers; half page g of page p lives in buffer 2(p&1)+g.  Epilogue warps 8g..8g+7 process the half pages g: warp w
+// reads TMEM lanes 32(w%4)..+31 (thread = query) and 64 of the buffer's 128 columns; survivors go into the warp's ring.
+// Two issue streams and two double-buffered epilogue groups hide the hand-off latencies (mbarrier waits, MMA issue,
+// commits: ~900 cycles per page for a single issuer).  The last four warps are the RESCORERS: rescorer r consumes the rings of
+// the four epilogue warps of lane quadrant r, re-evaluates the survivors exactly, owns the quadrant's 32 top-K lists
+// (no locks) and publishes the tightened bounds, so the MMA->epilogue pipeline never waits for an exact evaluation.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -39,7 +39,8 @@ constexpr int kTcQ = 128;          // queries per tile (MMA M)
 constexpr int kTcKSlice = 32;      // K elements (FP16) per shared-memory stage: 16 KB
 constexpr int kTcMaxStages = 6;    // slice stages (fewer when K is large and the lists need the shared memory)
 constexpr int kTcEpiWarps = 16;
-constexpr int kTcThreads = (kTcEpiWarps + 1 + 4 + 4) * 32;  // + producer, 4 MMA issuers, 4 rescorers
+constexpr int kTcMaxMmaWarps = 4;  // MMA issuers: 2 (one per page parity; narrow points, one K slice per page) or 4 (one per TMEM buffer)
+__host__ __device__ constexpr int tc_threads(int n_iss) { return (kTcEpiWarps + 1 + n_iss + 4) * 32; }  // + producer, MMA issuers, 4 rescorers
 constexpr int kTcQueueCap = 256;   // ring entries per epilogue warp (power of two)
 
 struct TcScanParams {
@@ -193,7 +194,10 @@ __device__ __forceinline__ float fmin2f(float a, float b) {
     asm("min.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
     return d;
 }
-__global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP) {
+// N_ISS = MMA issuer warps: 2 (23 warps: 80 registers per thread, the min trees keep their values in registers) or 4 (25 warps, 72)
+template <int N_ISS>
+__global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanParams TP) {
+    static_assert(N_ISS == 2 || N_ISS == 4, "issuers: one per page parity or one per TMEM buffer");
     const ScanParams& P = TP.S;
     const DevTree& T = P.T;
     const int dpad = T.dpad, K = P.K, kp = TP.kp;
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             mbar_init(&full_b[s], 1);
-            mbar_init(&empty_b[s], 2);  // one commit per MMA warp
+            mbar_init(&empty_b[s], N_ISS / 2);  // one commit per issuer that reads the stage
         }
         for (int b = 0; b < 4; b++) {
             mbar_init(&tfull_b[b], 1);
@@ -319,23 +323,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                 ppg++;
             }
         }
-    } else if (warp > kTcEpiWarps && warp <= kTcEpiWarps + 4) {
-        // ================= MMA issuers: warp 17+g issues the MMAs of half page g; the whole warp walks the pipeline,
-        // one elected lane issues (keeps tcgen05 on the uniform datapath) =================
-        // one issuer per TMEM buffer: warp 17+m issues half page g = m&1 of the pages with parity m>>1 (buffer 2*(m>>1)+g);
-        // the hand-off latencies of consecutive pages (mbarrier waits, MMA issue, commits) then overlap
-        const int g = (warp - (kTcEpiWarps + 1)) & 1, my_par = (warp - (kTcEpiWarps + 1)) >> 1;
+    } else if (warp > kTcEpiWarps && warp <= kTcEpiWarps + N_ISS) {
+        // ================= MMA issuers: warp 17+b issues the pages of parity b (half page h -> TMEM buffer 2b+h); the whole warp walks the pipeline,
+        // one elected lane issues (keeps tcgen05 on the uniform datapath).  Several issuers, so the hand-off latencies of
+        // consecutive pages (mbarrier waits, MMA issue, commits) overlap =================
+        // n_iss == 2: warp 17+b issues both half pages of the pages with parity b (3 % faster on one-slice pages);
+        // n_iss == 4: warp 17+m issues half page m&1 of the pages with parity m>>1 (7 % faster when a page has several K slices)
+        const int m_iss = warp - (kTcEpiWarps + 1);
+        const int my_par = (N_ISS == 2) ? m_iss : (m_iss >> 1);
+        const int h_lo = (N_ISS == 2) ? 0 : (m_iss & 1), h_hi = (N_ISS == 2) ? 1 : (m_iss & 1);
         constexpr int kHalf = kPage / 2;  // N of one MMA: a half page
         // kind::f16: D = F32 (1<<4), A = B = F16 (format 0), K-major both, N>>3, M>>4
         const uint32_t idesc = (1u << 4) | ((uint32_t)(kHalf >> 3) << 17) | ((uint32_t)(kTcQ >> 4) << 24);
-        // Descriptors are affine in (slice, k16, stage): two bases built once plus 16-byte-unit offsets.
+        // Descriptors are affine in (slice, k16, stage, half): two bases built once plus 16-byte-unit offsets.
         constexpr uint32_t kAStep = 2 * (kTcQ / 8) * 128 / 16;   // two K chunks (16 halves) of the A image, in 16-byte units
         constexpr uint32_t kBStep = 2 * (kPage / 8) * 128 / 16;  // two K chunks of a B stage
         constexpr uint32_t kBHalf = (kHalf / 8) * 128 / 16;      // second half page inside a K chunk
         const uint32_t kBStage = stage_bytes / 16;
         const uint64_t da0 = umma_desc_kmajor(smem_u32(sA), (kTcQ / 8) * 128, 128);
-        const uint64_t db0 = umma_desc_kmajor(smem_u32(stage_mem), (kPage / 8) * 128, 128) + (uint64_t)((uint32_t)g * kBHalf);
-        uint32_t st = 0, ph = 0, pg = 0;
+        const uint64_t db0 = umma_desc_kmajor(smem_u32(stage_mem), (kPage / 8) * 128, 128);
+        const uint32_t d_tmem = tmem + (uint32_t)my_par * kPage;  // buffers 2*par (half 0) and 2*par+1 (half 1)
+        uint64_t* const tfull_p = &tfull_b[2 * my_par];
+        uint64_t* const tempty_p = &tempty_b[2 * my_par];
+        uint32_t st = 0, ph = 0, pg = 0, use_ph = 1;  // use_ph: parity to wait for on tempty (the first use passes immediately)
         auto advance = [&](uint32_t k) {
             st += k;
             while (st >= (uint32_t)n_stages) {
@@ -349,36 +359,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_scan_tc(const TcScanParams TP
                 pg++;
                 continue;
             }
-            // half page g of page pg -> buffer 2*(pg&1)+g, used for the (pg>>1)-th time
-            const uint32_t buf = 2 * (pg & 1) + g;
-            const uint32_t d_tmem = tmem + buf * kHalf;
-            mbar_wait(&tempty_b[buf], ((pg >> 1) & 1) ^ 1);
-            TC_STAMP(g == 0, pg, 2);
             for (int s = 0; s < n_slices; s++) {
                 mbar_wait(&full_b[st], ph);
-                TC_STAMP(g == 0 && s == 0, pg, 3);
-                tc_fence_after();
+                TC_STAMP(s == 0, pg, 3);
                 const int n16 = min(kTcKSlice, kp - s * kTcKSlice) / 16;
                 const uint64_t da_s = da0 + (uint64_t)((uint32_t)s * (kTcKSlice / 16) * kAStep);
                 const uint64_t db_s = db0 + (uint64_t)(st * kBStage);
-                if (elect_one_sync()) {
+                for (int h = h_lo; h <= h_hi; h++) {
+                    if (s == 0) mbar_wait(&tempty_p[h], use_ph);  // the half's epilogue warps have read its previous page
+                    TC_STAMP(s == 0 && h == 0, pg, 2);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
 #pragma unroll 2
-                    for (int k16 = 0; k16 < n16; k16++)
-                        umma_f16(d_tmem, da_s + (uint64_t)((uint32_t)k16 * kAStep), db_s + (uint64_t)((uint32_t)k16 * kBStep), idesc,
-                                 (s > 0 || k16 > 0) ? 1u : 0u);
-                    if (s == n_slices - 1) umma_commit(&tfull_b[buf]);
-                    umma_commit(&empty_b[st]);  // the stage may be refilled once both half pages' MMAs have read it
+                        for (int k16 = 0; k16 < n16; k16++)
+                            umma_f16(d_tmem + h * kHalf, da_s + (uint64_t)((uint32_t)k16 * kAStep),
+                                     db_s + (uint64_t)((uint32_t)k16 * kBStep + (uint32_t)h * kBHalf), idesc, (s > 0 || k16 > 0) ? 1u : 0u);
+                        if (s == n_slices - 1) umma_commit(&tfull_p[h]);
+                        if (h == h_hi) umma_commit(&empty_b[st]);  // the stage may be refilled once both half pages' MMAs have read it
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
                 advance(1);
             }
-            TC_STAMP(g == 0, pg, 4);
+            use_ph ^= 1;
+            TC_STAMP(true, pg, 4);
             pg++;
         }
     } else {
         // epilogue warps and rescorers share the per-query filter constants: thread = query of the lane quadrant
         const bool is_epi = warp < kTcEpiWarps;
-        const int quad = is_epi ? (warp & 3) : (warp - (kTcEpiWarps + 5));
+        const int quad = is_epi ? (warp & 3) : (warp - (kTcEpiWarps + 1 + N_ISS));
         const int qi = quad * 32 + lane;  // tile-local query
         const bool valid_q = qi < nq_tile;
         float qn2 = 0.f, s1 = 0.f, l1 = 0.f, amax = 0.f;
