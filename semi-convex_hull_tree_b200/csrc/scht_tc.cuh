@@ -403,14 +403,14 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
         const bool in_range = 2.f * amax * scale < 60000.f;
         const float margin = tc_margin(s1 * 1.0001f, sqrtf(qn2) * 1.0001f, l1 * 1.0001f, TP.pnorm_max, TP.pabs_sum, scale) + qn2 * 1.0e-5f;
         const float s2 = scale * scale;
-        const float pad_bound = 40000.f * TP.norm_unit;  // real points stay below 32768 u + |G|, padded ones sit at 60000 u
         auto bound_of = [&](float kth) {
             // S passes when S <= s^2 (kth(1+2^-20) - |q'|^2 + margin); padded query slots never pass; a query outside
-            // FP16's range has a zero operand row and lets every real point pass
-            // (the norm slots of padded positions hold 60000 u, above every real s^2|p'|^2 and above pad_bound)
+            // FP16's range has a zero operand row and lets everything pass.  The bound is NOT clamped below the norm slots
+            // of padded positions (60000 u): a real pair of a far query can lie above any such clamp, and a padded position
+            // that passes (only the last page has them) is rejected by the exact evaluation (its distance is +inf).
             if (!valid_q) return -3.0e38f;
-            if (!in_range) return pad_bound;
-            return fminf((fminf(kth * 1.000001f, 3.0e38f) - qn2 + margin) * s2, pad_bound);
+            if (!in_range) return 3.0e38f;
+            return (fminf(kth * 1.000001f, 3.0e38f) - qn2 + margin) * s2;
         };
 
         if (!is_epi) {
