@@ -364,13 +364,14 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             size_t smem = tc_smem_bytes(T.dpad, h->kp, K, tc_stages);
             int n_iss = (h->kp <= kTcKSlice) ? 2 : 4;  // one K slice per page: two issuers (+3 %); several: four (+7 %)
             if (h->tc_issuers == 2 || h->tc_issuers == 4) n_iss = h->tc_issuers;  // SCHT_TC_ISSUERS
-            if (n_iss == 2) {
-                CU_TRY(cudaFuncSetAttribute(k_scan_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_scan_tc<2><<<n_tiles_main * n_seg, tc_threads(2), smem, s>>>(TC);
-            } else {
-                CU_TRY(cudaFuncSetAttribute(k_scan_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_scan_tc<4><<<n_tiles_main * n_seg, tc_threads(4), smem, s>>>(TC);
-            }
+            auto launch_tc = [&](auto kernel, int threads) {
+                cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e == cudaSuccess) kernel<<<n_tiles_main * n_seg, threads, smem, s>>>(TC);
+                return e;
+            };
+            const bool rows = T.rows != nullptr;  // wide points: exact re-evaluation from the row-major copy
+            if (n_iss == 2) CU_TRY(rows ? launch_tc(k_scan_tc<2, true>, tc_threads(2)) : launch_tc(k_scan_tc<2, false>, tc_threads(2)));
+            else CU_TRY(rows ? launch_tc(k_scan_tc<4, true>, tc_threads(4)) : launch_tc(k_scan_tc<4, false>, tc_threads(4)));
             CU_TRY(cudaGetLastError());
             if (n_seg > 1) {
                 k_merge_partial<<<(nq + 127) / 128, 128, 0, s>>>(T, h->seg_keys.as<uint64_t>(), n_seg, nq, K, P.idx_out, P.d2_out, P.dist_out);
@@ -649,7 +650,7 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
         T.xnorm_max = (float)(std::sqrt(mx) * 1.0001);
         if (!(T.xnorm_max < 3.0e38f)) T.xnorm_max = 3.0e38f;
     }
-    // pages: upload row-major slabs and transpose on the device
+    // pages: upload row-major slabs, transpose on the device (and keep a padded row-major copy)
     {
         float* pages = nullptr;
         size_t pbytes = (size_t)T.n_pages * dpad * kPage * 4;
@@ -657,6 +658,15 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
         h->owned.push_back(pages);
         h->tree_bytes += pbytes;
         T.pages = pages;
+        // wide points (several 16 KB slices per page): the same padded values row-major, for the exact re-evaluation of single
+        // points.  Narrow points are re-evaluated from the stage in shared memory (k_scan) or the L2-resident pages (k_scan_tc)
+        float* rows = nullptr;
+        if (dpad > kRowsPerStage) {
+            CU_H(cudaMalloc(&rows, pbytes));
+            h->owned.push_back(rows);
+            h->tree_bytes += pbytes;
+        }
+        T.rows = rows;
         const int64_t slab = 4 << 20;  // rows per slab
         DevBuf tmp;
         CU_H(tmp.reserve((size_t)std::min<int64_t>(slab, (int64_t)T.n_pages * kPage) * dim * 4));
@@ -666,7 +676,7 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
             int64_t real = std::max<int64_t>(0, std::min<int64_t>(nr, N - r0));
             if (real > 0) CU_H(cudaMemcpyAsync(tmp.p, t->sorted_points + (size_t)r0 * dim, (size_t)real * dim * 4, cudaMemcpyHostToDevice, h->stream));
             int64_t work = nr * dpad;
-            k_build_pages<<<(unsigned)((work + 255) / 256), 256, 0, h->stream>>>(tmp.as<float>(), r0, nr, dim, dpad, N, pages);
+            k_build_pages<<<(unsigned)((work + 255) / 256), 256, 0, h->stream>>>(tmp.as<float>(), r0, nr, dim, dpad, N, pages, rows);
             CU_H(cudaGetLastError());
             CU_H(cudaStreamSynchronize(h->stream));
         }

@@ -53,6 +53,7 @@ struct __align__(32) NodeRec {
 struct DevTree {
     int dim, dpad, n_points, n_pages, n_nodes, n_leaves;
     const float* pages;       // [n_pages][dpad][256]
+    const float* rows;        // [n_pages*256][dpad] the same values row-major when dpad > 16 (else null): an exact re-evaluation reads ONE point
     const int* orig_idx;      // [n_pages*256], -1 on padded positions
     const NodeRec* nodes;     // [n_nodes]
     const float* node_beta;   // CSR by NodeRec::beta_off, root-side constraint first
@@ -153,12 +154,17 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
 
 // The reference's accumulation step: result(float) += pow(d, 2) evaluated in double (Code/basic_functions.h:177,194).
 __device__ __forceinline__ float ref_acc_sq(float acc, float d) { return (float)((double)acc + (double)d * (double)d); }
+// A wide point's row spans several 128-byte lines: ask for all of them before the dependent chain walks the row, so the
+// chain pays one memory round trip instead of one per batch of loads
+__device__ __forceinline__ void prefetch_row(const float4* row, int dpad) {
+    for (int c = 8; c < dpad / 4; c += 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + c));
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // page builder: row-major sorted points -> dim-major pages
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_build_pages(const float* __restrict__ rows, int64_t row0, int64_t nrows, int dim, int dpad, int64_t n_points,
-                              float* __restrict__ pages) {
+                              float* __restrict__ pages, float* __restrict__ rows_out) {
     // one thread per (position, dim) of the pages touched by rows [row0, row0+nrows) rounded to pages
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = nrows * dpad;
@@ -170,6 +176,7 @@ __global__ void k_build_pages(const float* __restrict__ rows, int64_t row0, int6
     int64_t page = pos / kPage;
     int lane = (int)(pos - page * kPage);
     pages[(page * dpad + j) * kPage + lane] = v;
+    if (rows_out) rows_out[pos * dpad + j] = v;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -677,18 +684,31 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
                             bits &= bits - 1;
                             int in_page = ((e >> 2) ? 128 : 0) + 4 * lane + (e & 3);
                             pos = page * kPage + in_page;
-                            const float* pg = hold_stage ? stage_mem + (size_t)held_st * kRowsPerStage * kPage + in_page
-                                                         : T.pages + (size_t)page * dpad * kPage + in_page;
                             const float* qq = qs + qw0 + qi;
                             // loads first (8 dims in flight), then the sequential reference chain: the chain would otherwise
-                            // serialise one L2 round trip per dimension
-                            for (int j0 = 0; j0 < T.dim; j0 += 8) {
-                                float pv[8];
+                            // serialise one round trip per dimension.  A held stage is read from shared memory (dim-major);
+                            // otherwise the point's row comes from the row-major copy (two 16-byte loads per 8 dims)
+                            if (hold_stage) {
+                                const float* pg = stage_mem + (size_t)held_st * kRowsPerStage * kPage + in_page;
+                                for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                                    float pv[8];
 #pragma unroll
-                                for (int u = 0; u < 8; u++) pv[u] = (j0 + u < T.dim) ? pg[(size_t)(j0 + u) * kPage] : 0.f;
+                                    for (int u = 0; u < 8; u++) pv[u] = (j0 + u < T.dim) ? pg[(size_t)(j0 + u) * kPage] : 0.f;
 #pragma unroll
-                                for (int u = 0; u < 8; u++)
-                                    if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
+                                    for (int u = 0; u < 8; u++)
+                                        if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
+                                }
+                            } else {
+                                const float4* pr = reinterpret_cast<const float4*>(T.rows + (size_t)pos * dpad);
+                                prefetch_row(pr, dpad);
+                                for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                                    const float4 x = __ldg(pr + (j0 >> 2));
+                                    const float4 y = (j0 + 4 < dpad) ? __ldg(pr + (j0 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                    const float pv[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+                                    for (int u = 0; u < 8; u++)
+                                        if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
+                                }
                             }
                             n_exact++;
                             cand = (d2 < 3.402823466e+38f) && (pos >= P.pos_lo) && (pos < P.pos_hi);

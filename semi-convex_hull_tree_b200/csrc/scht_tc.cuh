@@ -195,7 +195,9 @@ __device__ __forceinline__ float fmin2f(float a, float b) {
     return d;
 }
 // N_ISS = MMA issuer warps: 2 (23 warps: 80 registers per thread, the min trees keep their values in registers) or 4 (25 warps, 72)
-template <int N_ISS>
+// ROWS = the rescorers read wide points from the row-major copy (T.rows); a compile-time choice because the pipeline is
+// sensitive to the kernel's code size (both paths in one kernel cost 2.5 % on 16-dimensional points)
+template <int N_ISS, bool ROWS>
 __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanParams TP) {
     static_assert(N_ISS == 2 || N_ISS == 4, "issuers: one per page parity or one per TMEM buffer");
     const ScanParams& P = TP.S;
@@ -423,18 +425,20 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             volatile int* v_done = q_done;
             volatile float* v_tq = tq_s;
             unsigned int n_exact = 0, n_ins = 0;
-            int heads[4] = {0, 0, 0, 0};
             v_tq[qi] = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));  // bounds from the seed scan
             __threadfence_block();
             asm volatile("bar.sync %0, 160;" ::"r"(1 + quad) : "memory");  // ... visible to the quadrant's 4 epilogue warps
             for (;;) {
                 bool all_done = true, did_work = false;
-#pragma unroll
+                // one copy of the loop body (not unrolled: four copies of the evaluation + insertion code cost the pipeline
+                // warps instruction-cache misses); a ring's head lives in shared memory, this warp is its only writer
+#pragma unroll 1
                 for (int i = 0; i < 4; i++) {
                     const int w = quad + 4 * i;  // epilogue warp ids of this quadrant: quad, quad+4, quad+8, quad+12
                     const int done = v_done[w];
                     const int tail = v_tail[w];
-                    const int avail = tail - heads[i];
+                    const int head = v_head[w];
+                    const int avail = tail - head;
                     all_done &= (done != 0) && (avail == 0);
                     if (avail == 0) continue;
                     did_work = true;
@@ -445,32 +449,52 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                     float d2 = 0.f;
                     int pos = 0, cq = 0;
                     if (lane < n) {
-                        const uint64_t e = ring[(heads[i] + lane) & (kTcQueueCap - 1)];
+                        const uint64_t e = ring[(head + lane) & (kTcQueueCap - 1)];
                         pos = (int)(uint32_t)e;
                         cq = (int)(e >> 32);
-                        const int pgi = pos / kPage;
-                        const float* pg = T.pages + (size_t)pgi * dpad * kPage + (pos - pgi * kPage);
                         const float* qq = P.q + (size_t)qids[quad * 32 + cq] * T.dim;  // the query's original coordinates
-                        // loads first (8 dims at a time), then the sequential reference chain
-                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
-                            float pv[8], qv[8];
+                        if constexpr (ROWS) {
+                            // wide points: the row-major copy (dpad*4 contiguous bytes; the dim-major pages cost one 32-byte
+                            // sector per coordinate).  Loads first (16 dims at a time), then the sequential reference chain
+                            const float4* pr = reinterpret_cast<const float4*>(T.rows + (size_t)pos * dpad);
+                            prefetch_row(pr, dpad);
+                            for (int j0 = 0; j0 < T.dim; j0 += 16) {
+                                float pv[16], qv[16];
 #pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                const bool in = j0 + u < T.dim;
-                                pv[u] = in ? pg[(size_t)(j0 + u) * kPage] : 0.f;
-                                qv[u] = in ? qq[j0 + u] : 0.f;
+                                for (int u = 0; u < 4; u++) {
+                                    const float4 x = (j0 + 4 * u < dpad) ? __ldg(pr + (j0 >> 2) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                    pv[4 * u] = x.x, pv[4 * u + 1] = x.y, pv[4 * u + 2] = x.z, pv[4 * u + 3] = x.w;
+                                }
+#pragma unroll
+                                for (int u = 0; u < 16; u++) qv[u] = (j0 + u < T.dim) ? qq[j0 + u] : 0.f;
+#pragma unroll
+                                for (int u = 0; u < 16; u++)
+                                    if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qv[u]);
                             }
+                        } else {
+                            // narrow points (one 16 KB page slice): the dim-major page the seed scan left in L2
+                            const int pgi = pos / kPage;
+                            const float* pg = T.pages + (size_t)pgi * dpad * kPage + (pos - pgi * kPage);
+                            for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                                float pv[8], qv[8];
 #pragma unroll
-                            for (int u = 0; u < 8; u++)
-                                if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qv[u]);
+                                for (int u = 0; u < 8; u++) {
+                                    const bool in = j0 + u < T.dim;
+                                    pv[u] = in ? pg[(size_t)(j0 + u) * kPage] : 0.f;
+                                    qv[u] = in ? qq[j0 + u] : 0.f;
+                                }
+#pragma unroll
+                                for (int u = 0; u < 8; u++)
+                                    if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qv[u]);
+                            }
                         }
                         n_exact++;
                         cand = (d2 < 3.402823466e+38f) && (pos >= P.pos_lo) && (pos < P.pos_hi);
                         if (cand) cand = ((uint64_t)__float_as_uint(d2) << 32) <= lists[(size_t)(quad * 32 + cq) * K + K - 1];
                     }
                     __syncwarp();
-                    heads[i] += n;
-                    if (lane == 0) v_head[w] = heads[i];  // the ring slots may be reused (values are in registers now)
+                    if (lane == 0) v_head[w] = head + n;  // the ring slots may be reused (values are in registers now)
+                    __syncwarp();  // ... and every lane reads the new head on the ring's next visit
                     unsigned m = __ballot_sync(0xffffffffu, cand);
                     while (m) {
                         int src = __ffs(m) - 1;
