@@ -68,6 +68,10 @@ struct scht_handle {
     int64_t batch_size = 1000000;  // Code/main.cc:670
     int scan_variant = 2;
     int traverse_sampling = 1;    // sample the traversal before running it for every tile (SCHT_TRAVERSE_SAMPLING=0 disables)
+    int sample_reuse = 7;         // after two consecutive batches whose sample said "list every page", the next n batches of the same
+    int sample_streak = 0;        //   shape skip the sample (SCHT_SAMPLE_REUSE, 0 = sample every batch); results never depend on it
+    int sample_skip = 0;
+    long long sample_sig = -1;
     int tc_mode = 2;              // tensor-core prefilter: 0 off, 1 always, 2 auto (per batch, from the seed bounds)
     int tc_split = 1;             // page segments per prefilter tile: 0 never split, 1 auto, n > 1 forced (SCHT_TC_SPLIT)
     int tc_issuers = 0;           // MMA issuer warps of k_scan_tc: 0 auto (2 for one K slice per page, else 4), or 2 / 4 (SCHT_TC_ISSUERS)
@@ -279,7 +283,15 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         // other tiles (all their pages are listed); otherwise the remaining tiles are traversed too.
         // (about 24 sampled tiles, at least every 64th and at most every 8th tile)
         const int kSample = std::max(8, std::min(64, n_tiles_main / 24));
-        if (n_tiles_main >= 64 && h->traverse_sampling) {
+        const int page_lo = P.pos_lo / kPage, page_hi = (P.pos_hi + kPage - 1) / kPage;
+        const long long sig = (long long)use_tc | ((long long)K << 1) | ((long long)leaf_lo << 12) | ((long long)leaf_hi << 36);
+        if (n_tiles_main >= 64 && h->traverse_sampling && h->sample_skip > 0 && sig == h->sample_sig) {
+            // the samples of the last batches of this shape all kept (nearly) every page: list them without asking again
+            h->sample_skip--;
+            k_list_all<<<(n_tiles_main + 127) / 128, 128, 0, s>>>(h->ranges.as<int2>(), h->n_ranges.as<int>(), n_tiles_main, T.n_cuts, 0, 1, page_lo, page_hi);
+            CU_TRY(cudaGetLastError());
+            launches++;
+        } else if (n_tiles_main >= 64 && h->traverse_sampling) {
             unsigned long long before = 0, after = 0;
             TP.sel_mode = 1;
             TP.sel_step = kSample;
@@ -290,7 +302,6 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             CU_TRY(cudaStreamSynchronize(s));
             long long sampled_q = 0;
             for (int t = 0; t < n_tiles_main; t += kSample) sampled_q += std::min(tq_main, nq - t * tq_main);
-            const int page_lo = P.pos_lo / kPage, page_hi = (P.pos_hi + kPage - 1) / kPage;
             const double kept = (double)(after - before) / std::max(1.0, (double)sampled_q * std::max(1, page_hi - page_lo));
             TP.sel_mode = 2;
             // a prefilter page costs ~1/10 of an exact page, so pruning must remove much more before it pays for itself
@@ -299,10 +310,14 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
                 k_list_all<<<(rest + 127) / 128, 128, 0, s>>>(h->ranges.as<int2>(), h->n_ranges.as<int>(), n_tiles_main, T.n_cuts, 2, kSample, page_lo,
                                                              page_hi);
                 CU_TRY(cudaGetLastError());
+                if (sig != h->sample_sig) h->sample_streak = 0;
+                if (++h->sample_streak >= 2) h->sample_skip = h->sample_reuse;
             } else {
                 rc = launch_traverse(h, TP, s);
                 if (rc) return rc;
+                h->sample_streak = 0;
             }
+            h->sample_sig = sig;
             launches++;
         } else {
             TP.sel_mode = 0;
@@ -684,6 +699,7 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     }
     // tensor-core page image (centred, TF32-rounded coordinates + |p'|^2 hi/lo), see scht_tc.cuh
     if (const char* ev = getenv("SCHT_TRAVERSE_SAMPLING")) h->traverse_sampling = atoi(ev) != 0;
+    if (const char* ev = getenv("SCHT_SAMPLE_REUSE")) h->sample_reuse = std::max(0, atoi(ev));
     if (const char* ev = getenv("SCHT_TC")) h->tc_mode = std::max(0, std::min(2, atoi(ev)));
     if (const char* ev = getenv("SCHT_TC_SPLIT")) h->tc_split = std::max(0, atoi(ev));
     if (const char* ev = getenv("SCHT_TC_ISSUERS")) h->tc_issuers = atoi(ev);

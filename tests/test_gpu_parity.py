@@ -246,3 +246,30 @@ def test_stats_surface(pkg):
     assert st["dist_computations"] > 0 and st["hyperplane_tests"] > 0 and st["descent_dists"] > 0 and st["list_insertions"] >= 30000
     assert st["ms_total"] >= st["ms_device"] > 0 and abs(st["ms_scan"] - st["ms_seed_scan"] - st["ms_main_scan"]) < 1e-3
     ix.close()
+
+
+@pytest.mark.parametrize("dim", [16, 40])
+def test_sample_reuse_and_wide_rows(pkg, monkeypatch, dim):
+    """repeated batches of one shape skip the traversal sample after two "list every page" verdicts (SCHT_SAMPLE_REUSE);
+    wide points (dim > 16) are re-evaluated from the row-major copy: every call must equal the exhaustive device scan"""
+    rng = np.random.default_rng(77 + dim)
+    data, q = rng.random((60000, dim), dtype=np.float32), rng.random((9000, dim), dtype=np.float32)
+    monkeypatch.setenv("SCHT_TC", "1")
+    ix = pkg.Index(pkg.HostTree(data, 0.004, seed=1))
+    bi, bd2 = ix.brute_force(q, 10)
+    tests = []
+    for rep in range(4):
+        idx, d2, st = ix.query(q, 10, want_stats=True)
+        assert_bit_equal(idx, bi, "idx rep=%d" % rep)
+        assert_bit_equal(d2, bd2, "dist2 rep=%d" % rep)
+        assert st["prefilter_batches"] == 1
+        tests.append(st["hyperplane_tests"])
+    assert tests[0] == tests[1] and tests[2] <= tests[0] and tests[3] <= tests[0]
+    ix.close()
+    monkeypatch.setenv("SCHT_SAMPLE_REUSE", "0")
+    ix = pkg.Index(pkg.HostTree(data, 0.004, seed=1))
+    for rep in range(3):
+        idx, d2, st = ix.query(q, 10, want_stats=True)
+        assert_bit_equal(idx, bi, "idx (no reuse) rep=%d" % rep)
+        assert st["hyperplane_tests"] == tests[0]
+    ix.close()
