@@ -75,6 +75,7 @@ struct scht_handle {
     int tc_mode = 2;              // tensor-core prefilter: 0 off, 1 always, 2 auto (per batch, from the seed bounds)
     int tc_split = 1;             // page segments per prefilter tile: 0 never split, 1 auto, n > 1 forced (SCHT_TC_SPLIT)
     int tc_issuers = 0;           // MMA issuer warps of k_scan_tc: 0 auto (2 for one K slice per page, else 4), or 2 / 4 (SCHT_TC_ISSUERS)
+    int tc_n256 = 0;              // 1: with two issuers, one N=256 MMA chain per page instead of two N=128 chains (SCHT_TC_N256)
     int kp = 0;                   // padded K of the tensor-core page image (0: not built)
     const unsigned char* tcpages = nullptr;
     float tc_scale = 1.f, pabs_sum = 0.f, norm_unit = 1.f;
@@ -385,8 +386,10 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
                 return e;
             };
             const bool rows = T.rows != nullptr;  // wide points: exact re-evaluation from the row-major copy
-            if (n_iss == 2) CU_TRY(rows ? launch_tc(k_scan_tc<2, true>, tc_threads(2)) : launch_tc(k_scan_tc<2, false>, tc_threads(2)));
-            else CU_TRY(rows ? launch_tc(k_scan_tc<4, true>, tc_threads(4)) : launch_tc(k_scan_tc<4, false>, tc_threads(4)));
+            const bool n256 = n_iss == 2 && h->tc_n256 == 1;  // SCHT_TC_N256=1: one N=256 chain per page (two issuers)
+            if (n256) CU_TRY(rows ? launch_tc(k_scan_tc<2, true, true>, tc_threads(2)) : launch_tc(k_scan_tc<2, false, true>, tc_threads(2)));
+            else if (n_iss == 2) CU_TRY(rows ? launch_tc(k_scan_tc<2, true, false>, tc_threads(2)) : launch_tc(k_scan_tc<2, false, false>, tc_threads(2)));
+            else CU_TRY(rows ? launch_tc(k_scan_tc<4, true, false>, tc_threads(4)) : launch_tc(k_scan_tc<4, false, false>, tc_threads(4)));
             CU_TRY(cudaGetLastError());
             if (n_seg > 1) {
                 k_merge_partial<<<(nq + 127) / 128, 128, 0, s>>>(T, h->seg_keys.as<uint64_t>(), n_seg, nq, K, P.idx_out, P.d2_out, P.dist_out);
@@ -703,6 +706,7 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     if (const char* ev = getenv("SCHT_TC")) h->tc_mode = std::max(0, std::min(2, atoi(ev)));
     if (const char* ev = getenv("SCHT_TC_SPLIT")) h->tc_split = std::max(0, atoi(ev));
     if (const char* ev = getenv("SCHT_TC_ISSUERS")) h->tc_issuers = atoi(ev);
+    if (const char* ev = getenv("SCHT_TC_N256")) h->tc_n256 = atoi(ev);
     {
         const int kp = (dim + 3 + 15) & ~15;
         const size_t tbytes = (size_t)T.n_pages * tc_page_bytes(kp);

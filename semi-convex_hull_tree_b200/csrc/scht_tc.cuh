@@ -197,9 +197,12 @@ __device__ __forceinline__ float fmin2f(float a, float b) {
 // N_ISS = MMA issuer warps: 2 (23 warps: 80 registers per thread, the min trees keep their values in registers) or 4 (25 warps, 72)
 // ROWS = the rescorers read wide points from the row-major copy (T.rows); a compile-time choice because the pipeline is
 // sensitive to the kernel's code size (both paths in one kernel cost 2.5 % on 16-dimensional points)
-template <int N_ISS, bool ROWS>
+// N256 (two issuers only) = one N=256 MMA chain per page instead of two N=128 chains (128 instead of 2 x 92 cycles per K16
+// step): both half-page buffers of the page's parity are filled and committed together; the epilogue is unchanged
+template <int N_ISS, bool ROWS, bool N256>
 __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanParams TP) {
     static_assert(N_ISS == 2 || N_ISS == 4, "issuers: one per page parity or one per TMEM buffer");
+    static_assert(!N256 || N_ISS == 2, "whole-page chains: one issuer per page parity");
     const ScanParams& P = TP.S;
     const DevTree& T = P.T;
     const int dpad = T.dpad, K = P.K, kp = TP.kp;
@@ -367,6 +370,27 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                 const int n16 = min(kTcKSlice, kp - s * kTcKSlice) / 16;
                 const uint64_t da_s = da0 + (uint64_t)((uint32_t)s * (kTcKSlice / 16) * kAStep);
                 const uint64_t db_s = db0 + (uint64_t)(st * kBStage);
+                if constexpr (N256) {
+                    if (s == 0) {  // both halves' epilogue warps have read the previous page of this parity
+                        mbar_wait(&tempty_p[0], use_ph);
+                        mbar_wait(&tempty_p[1], use_ph);
+                    }
+                    TC_STAMP(s == 0, pg, 2);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t idesc256 = (1u << 4) | ((uint32_t)(kPage >> 3) << 17) | ((uint32_t)(kTcQ >> 4) << 24);
+#pragma unroll 2
+                        for (int k16 = 0; k16 < n16; k16++)
+                            umma_f16(d_tmem, da_s + (uint64_t)((uint32_t)k16 * kAStep), db_s + (uint64_t)((uint32_t)k16 * kBStep), idesc256,
+                                     (s > 0 || k16 > 0) ? 1u : 0u);
+                        if (s == n_slices - 1) {
+                            umma_commit(&tfull_p[0]);
+                            umma_commit(&tfull_p[1]);
+                        }
+                        umma_commit(&empty_b[st]);
+                    }
+                    __syncwarp();
+                } else
                 for (int h = h_lo; h <= h_hi; h++) {
                     if (s == 0) mbar_wait(&tempty_p[h], use_ph);  // the half's epilogue warps have read its previous page
                     TC_STAMP(s == 0 && h == 0, pg, 2);
