@@ -75,7 +75,7 @@ struct scht_handle {
     int tc_mode = 2;              // tensor-core prefilter: 0 off, 1 always, 2 auto (per batch, from the seed bounds)
     int tc_split = 1;             // page segments per prefilter tile: 0 never split, 1 auto, n > 1 forced (SCHT_TC_SPLIT)
     int tc_issuers = 0;           // MMA issuer warps of k_scan_tc: 0 auto (2 for one K slice per page, else 4), or 2 / 4 (SCHT_TC_ISSUERS)
-    int tc_n256 = 0;              // 1: with two issuers, one N=256 MMA chain per page instead of two N=128 chains (SCHT_TC_N256)
+    int tc_n256 = -1;             // one N=256 MMA chain per page (two issuers) instead of two N=128 chains: -1 auto (pages of several K slices), 0, 1 (SCHT_TC_N256)
     int kp = 0;                   // padded K of the tensor-core page image (0: not built)
     const unsigned char* tcpages = nullptr;
     float tc_scale = 1.f, pabs_sum = 0.f, norm_unit = 1.f;
@@ -378,7 +378,13 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
             }
             if (n_seg == 1) TC.n_seg = 1;
             size_t smem = tc_smem_bytes(T.dpad, h->kp, K, tc_stages);
-            int n_iss = (h->kp <= kTcKSlice) ? 2 : 4;  // one K slice per page: two issuers (+3 %); several: four (+7 %)
+            // One K slice per page (narrow points): two issuers, one per page parity, each issuing the page's two N=128 half-page
+            // chains (+3 % over four issuers; whole-page N=256 chains cost 2.4 % there).  Several slices per page (wide points): the
+            // MMA time counts, and one N=256 chain per page (128 instead of 2 x 92 cycles per K16 step) beats four issuers of
+            // half-page chains by 2 % (D=128) to 5 % (D=32).
+            const bool wide = h->kp > kTcKSlice;
+            bool want_n256 = (h->tc_n256 < 0) ? wide : (h->tc_n256 != 0);
+            int n_iss = (wide && !want_n256) ? 4 : 2;
             if (h->tc_issuers == 2 || h->tc_issuers == 4) n_iss = h->tc_issuers;  // SCHT_TC_ISSUERS
             auto launch_tc = [&](auto kernel, int threads) {
                 cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -386,7 +392,7 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
                 return e;
             };
             const bool rows = T.rows != nullptr;  // wide points: exact re-evaluation from the row-major copy
-            const bool n256 = n_iss == 2 && h->tc_n256 == 1;  // SCHT_TC_N256=1: one N=256 chain per page (two issuers)
+            const bool n256 = n_iss == 2 && want_n256;
             if (n256) CU_TRY(rows ? launch_tc(k_scan_tc<2, true, true>, tc_threads(2)) : launch_tc(k_scan_tc<2, false, true>, tc_threads(2)));
             else if (n_iss == 2) CU_TRY(rows ? launch_tc(k_scan_tc<2, true, false>, tc_threads(2)) : launch_tc(k_scan_tc<2, false, false>, tc_threads(2)));
             else CU_TRY(rows ? launch_tc(k_scan_tc<4, true, false>, tc_threads(4)) : launch_tc(k_scan_tc<4, false, false>, tc_threads(4)));
