@@ -448,32 +448,57 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             volatile int* v_head = q_head;
             volatile int* v_done = q_done;
             volatile float* v_tq = tq_s;
-            unsigned int n_exact = 0, n_ins = 0;
+            unsigned int n_exact = 0, n_ins = 0, rot = 0;
             v_tq[qi] = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));  // bounds from the seed scan
             __threadfence_block();
             asm volatile("bar.sync %0, 160;" ::"r"(1 + quad) : "memory");  // ... visible to the quadrant's 4 epilogue warps
             for (;;) {
-                bool all_done = true, did_work = false;
-                // one copy of the loop body (not unrolled: four copies of the evaluation + insertion code cost the pipeline
-                // warps instruction-cache misses); a ring's head lives in shared memory, this warp is its only writer
-#pragma unroll 1
-                for (int i = 0; i < 4; i++) {
-                    const int w = quad + 4 * i;  // epilogue warp ids of this quadrant: quad, quad+4, quad+8, quad+12
-                    const int done = v_done[w];
+                // One ROUND takes up to 32 entries from the quadrant's four rings together (lane -> ring by prefix sums of the
+                // available counts): the latency of an exact evaluation (loads + the sequential FP64 chain) is paid once per
+                // round whatever the number of entries, and a single ring rarely holds more than two or three.
+                // Fair when the rings are busy (large K): every ring gets 8 of the 32 lanes first, the rest goes to whoever has
+                // more, starting at a ring that rotates from round to round (a starved ring stalls its epilogue warp, hence the MMA).
+                bool all_done = true;
+                int head_r[4], n_r[4], avail_r[4], total = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {  // slot i = ring (i + rot) % 4
+                    const int w = quad + 4 * ((i + rot) & 3);  // epilogue warp ids of this quadrant: quad, quad+4, quad+8, quad+12
+                    const int done = v_done[w];  // (read before the tail: the warp publishes its last tail first)
                     const int tail = v_tail[w];
-                    const int head = v_head[w];
-                    const int avail = tail - head;
-                    all_done &= (done != 0) && (avail == 0);
-                    if (avail == 0) continue;
-                    did_work = true;
-                    __threadfence_block();  // entries below `tail` were written before it was published
-                    const int n = min(avail, 32);
-                    const uint64_t* ring = queues + (size_t)w * kTcQueueCap;
+                    head_r[i] = v_head[w];
+                    avail_r[i] = tail - head_r[i];
+                    all_done &= (done != 0) && (avail_r[i] == 0);
+                    n_r[i] = min(avail_r[i], 8);
+                    total += n_r[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int extra = min(avail_r[i] - n_r[i], 32 - total);
+                    n_r[i] += extra;
+                    total += extra;
+                }
+                if (total == 0) {
+                    if (all_done) break;
+                    __nanosleep(4000);  // survivors are rare (~1 per 10 pages and warp): poll seldom, the pipeline warps need the issue slots
+                    continue;
+                }
+                {
+                    __threadfence_block();  // entries below a `tail` were written before it was published
+                    int ri = 0, off = lane;
+#pragma unroll
+                    for (int i = 0; i < 3; i++)
+                        if (ri == i && off >= n_r[i]) {
+                            off -= n_r[i];
+                            ri = i + 1;
+                        }
+                    const int head = ri == 0 ? head_r[0] : ri == 1 ? head_r[1] : ri == 2 ? head_r[2] : head_r[3];
+                    const int n = total;
+                    const uint64_t* ring = queues + (size_t)(quad + 4 * ((ri + rot) & 3)) * kTcQueueCap;
                     bool cand = false;
                     float d2 = 0.f;
                     int pos = 0, cq = 0;
                     if (lane < n) {
-                        const uint64_t e = ring[(head + lane) & (kTcQueueCap - 1)];
+                        const uint64_t e = ring[(head + off) & (kTcQueueCap - 1)];
                         pos = (int)(uint32_t)e;
                         cq = (int)(e >> 32);
                         const float* qq = P.q + (size_t)qids[quad * 32 + cq] * T.dim;  // the query's original coordinates
@@ -517,8 +542,12 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                         if (cand) cand = ((uint64_t)__float_as_uint(d2) << 32) <= lists[(size_t)(quad * 32 + cq) * K + K - 1];
                     }
                     __syncwarp();
-                    if (lane == 0) v_head[w] = head + n;  // the ring slots may be reused (values are in registers now)
-                    __syncwarp();  // ... and every lane reads the new head on the ring's next visit
+                    if (lane < 4) {  // the ring slots may be reused (values are in registers now)
+                        const int nh = lane == 0 ? head_r[0] + n_r[0] : lane == 1 ? head_r[1] + n_r[1] : lane == 2 ? head_r[2] + n_r[2] : head_r[3] + n_r[3];
+                        v_head[quad + 4 * ((lane + rot) & 3)] = nh;
+                    }
+                    rot++;
+                    __syncwarp();  // ... and every lane reads the new heads in the next round
                     unsigned m = __ballot_sync(0xffffffffu, cand);
                     while (m) {
                         int src = __ffs(m) - 1;
@@ -535,8 +564,6 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                     // publish the (possibly) tightened bound of this lane's query
                     v_tq[qi] = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));
                 }
-                if (all_done) break;
-                if (!did_work) __nanosleep(4000);  // survivors are rare (~1 per 10 pages and warp): poll seldom, the pipeline warps need the issue slots
             }
             __syncwarp();
             // ---- results: the rescorer owns the lists of its 32 queries ----
