@@ -644,7 +644,9 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     {
         // seed neighbourhood of every leaf: the smallest enclosing subtree with >= kSeedPoints points
         std::vector<int> ss(L), se(L);
-        int seed_points = kSeedPoints;
+        // (wide points: the seed scan's exact evaluations cost a 128-step FP64 chain each; one tree level less -- 512 points -- took
+        // the SIFT-like 1Mx128 step from 46.7 to 44.0 ms)
+        int seed_points = (dpad >= 64) ? kSeedPoints / 2 : kSeedPoints;
         if (const char* ev = getenv("SCHT_SEED_POINTS")) seed_points = std::max(1, atoi(ev));
         for (int i = 0; i < nn; i++) {
             if (rec[i].leaf < 0) continue;
