@@ -67,6 +67,7 @@ struct scht_handle {
     size_t tree_bytes = 0;
     int64_t batch_size = 1000000;  // Code/main.cc:670
     int scan_variant = 2;
+    int scan_stages = 0;          // slice ring depth of k_scan's default variant: 0 auto, 2 or 4 (SCHT_SCAN_STAGES)
     int traverse_sampling = 1;    // sample the traversal before running it for every tile (SCHT_TRAVERSE_SAMPLING=0 disables)
     int sample_reuse = 7;         // after two consecutive batches whose sample said "list every page", the next n batches of the same
     int sample_streak = 0;        //   shape skip the sample (SCHT_SAMPLE_REUSE, 0 = sample every batch); results never depend on it
@@ -113,13 +114,13 @@ int pick_variant(const scht_handle* h, int K) {
     return -1;
 }
 
-template <int NW, int MINB, bool FULL>
+template <int NW, int MINB, bool FULL, int STAGES = kStages>
 int launch_scan_t(scht_handle* h, const ScanParams& P, cudaStream_t s) {
-    size_t smem = scan_smem_bytes(NW, P.T.dpad, P.K);
-    CU_TRY(cudaFuncSetAttribute(k_scan<NW, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = scan_smem_bytes(NW, P.T.dpad, P.K, STAGES);
+    CU_TRY(cudaFuncSetAttribute(k_scan<NW, MINB, FULL, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int tq = NW * kQPerWarp;
     int n_tiles = (P.nq + tq - 1) / tq;
-    k_scan<NW, MINB, FULL><<<n_tiles, (NW + 1) * 32, smem, s>>>(P);
+    k_scan<NW, MINB, FULL, STAGES><<<n_tiles, (NW + 1) * 32, smem, s>>>(P);
     CU_TRY(cudaGetLastError());
     return SCHT_OK;
 }
@@ -128,7 +129,14 @@ int launch_scan(scht_handle* h, int variant, const ScanParams& P, cudaStream_t s
     switch (variant) {
         case 0: return full ? launch_scan_t<8, 1, true>(h, P, s) : launch_scan_t<8, 1, false>(h, P, s);
         case 1: return full ? launch_scan_t<7, 2, true>(h, P, s) : launch_scan_t<7, 2, false>(h, P, s);
-        default: return full ? launch_scan_t<4, 3, true>(h, P, s) : launch_scan_t<4, 3, false>(h, P, s);
+        default: {
+            // three resident CTAs per SM are what hides the exact path's FP64 chains: when the query block of wide points makes a
+            // 4-stage CTA too big for that (D >= 64), a 2-stage ring brings the third CTA back
+            const size_t per_sm = 233472 - 3 * 1024;
+            const bool shallow = 3 * scan_smem_bytes(4, P.T.dpad, P.K) > per_sm && 3 * scan_smem_bytes(4, P.T.dpad, P.K, 2) <= per_sm && h->scan_stages != 4;
+            if (shallow || h->scan_stages == 2) return full ? launch_scan_t<4, 3, true, 2>(h, P, s) : launch_scan_t<4, 3, false, 2>(h, P, s);
+            return full ? launch_scan_t<4, 3, true>(h, P, s) : launch_scan_t<4, 3, false>(h, P, s);
+        }
     }
 }
 
@@ -714,6 +722,7 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     if (const char* ev = getenv("SCHT_TC")) h->tc_mode = std::max(0, std::min(2, atoi(ev)));
     if (const char* ev = getenv("SCHT_TC_SPLIT")) h->tc_split = std::max(0, atoi(ev));
     if (const char* ev = getenv("SCHT_TC_ISSUERS")) h->tc_issuers = atoi(ev);
+    if (const char* ev = getenv("SCHT_SCAN_STAGES")) h->scan_stages = atoi(ev);
     if (const char* ev = getenv("SCHT_TC_N256")) h->tc_n256 = atoi(ev);
     {
         const int kp = (dim + 3 + 15) & ~15;

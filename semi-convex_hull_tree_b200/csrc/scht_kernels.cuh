@@ -287,13 +287,13 @@ struct ScanParams {
     unsigned long long* counters;  // [0] scanned (query,point) pairs, [1] exact re-evaluations, [2] list insertions
 };
 
-__host__ __device__ inline size_t scan_smem_bytes(int n_cwarps, int dpad, int K) {
+__host__ __device__ inline size_t scan_smem_bytes(int n_cwarps, int dpad, int K, int stages = kStages) {
     size_t tq = (size_t)n_cwarps * kQPerWarp;
-    size_t b = (size_t)kStages * kRowsPerStage * kPage * 4;  // stages
+    size_t b = (size_t)stages * kRowsPerStage * kPage * 4;  // stages
     b += (size_t)dpad * tq * 4;                              // queries, dim-major
     b += tq * (size_t)K * 8;                                 // lists
     b += tq * 8 + tq * 5 * 4 + 16;                           // seed ranges, a0, a1, s0, s1, qid, misc
-    b += 2 * kStages * 8 + 64;                               // barriers
+    b += 2 * stages * 8 + 64;                                // barriers
     return b;
 }
 
@@ -405,14 +405,15 @@ struct PageWalk {
 };
 
 // FULL: dpad is a multiple of 16, every stage holds 16 rows and the row loop is straight-line code.
-template <int NW, int MINB, bool FULL>
+// STAGES: depth of the slice ring (4; 2 for wide points, whose query block would otherwise cost the third resident CTA).
+template <int NW, int MINB, bool FULL, int STAGES = kStages>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P) {
     constexpr int TQ = NW * kQPerWarp;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const DevTree& T = P.T;
     const int dpad = T.dpad, K = P.K;
     float* stage_mem = reinterpret_cast<float*>(smem_raw);
-    float* qs = stage_mem + kStages * kRowsPerStage * kPage;  // [dpad][TQ]
+    float* qs = stage_mem + STAGES * kRowsPerStage * kPage;  // [dpad][TQ]
     uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)dpad * TQ);
     int2* seed_rg = reinterpret_cast<int2*>(lists + (size_t)TQ * K);  // [TQ]
     int* a0s = reinterpret_cast<int*>(seed_rg + TQ);
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
     int* qids = s1s + TQ;
     int* misc = qids + TQ;  // [0] number of seed ranges
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc + 4);
-    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* empty_bar = full_bar + STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
 
     // ---- tile set-up -------------------------------------------------------------------------------------
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < STAGES; s++) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], NW);
         }
@@ -504,8 +505,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
             uint32_t it = 0;
             while (walk.next(page)) {
                 for (int s = 0; s < n_slices; s++, it++) {
-                    int st = it % kStages;
-                    uint32_t ph = (it / kStages) & 1;
+                    int st = it % STAGES;
+                    uint32_t ph = (it / STAGES) & 1;
                     mbar_wait_backoff(&empty_bar[st], ph ^ 1);
                     int rows = min(kRowsPerStage, dpad - s * kRowsPerStage);
                     uint32_t bytes = (uint32_t)rows * kPage * 4;
@@ -563,8 +564,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
 
         // one stage = one slice of <= 16 dimensions of the page; the first slice starts the accumulators
         auto stage_step = [&](int s, auto first) {
-            int st = it % kStages;
-            uint32_t ph = (it / kStages) & 1;
+            int st = it % STAGES;
+            uint32_t ph = (it / STAGES) & 1;
             mbar_wait(&full_bar[st], ph);
             const float* sp = stage_mem + (size_t)st * kRowsPerStage * kPage + 4 * lane;
             const float* qp = qs + (size_t)s * kRowsPerStage * TQ + qw0;
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
             if (!hold_stage && lane == 0) mbar_arrive(&empty_bar[st]);
             it++;
         };
-        const int held_st = it % kStages;  // (only meaningful when hold_stage)
+        const int held_st = it % STAGES;  // (only meaningful when hold_stage)
         stage_step(0, std::true_type{});
 #pragma unroll 1
         for (int s = 1; s < n_slices; s++) stage_step(s, std::false_type{});
