@@ -66,7 +66,7 @@ struct scht_handle {
     std::vector<void*> owned;  // device allocations of the tree
     size_t tree_bytes = 0;
     int64_t batch_size = 1000000;  // Code/main.cc:670
-    int scan_variant = 2;
+    int scan_variant = -1;        // k_scan shape (SCHT_SCAN_VARIANT): -1 auto, 0..3 see kVariantWarps
     int scan_stages = 0;          // slice ring depth of k_scan's default variant: 0 auto, 2 or 4 (SCHT_SCAN_STAGES)
     int traverse_sampling = 1;    // sample the traversal before running it for every tile (SCHT_TRAVERSE_SAMPLING=0 disables)
     int sample_reuse = 7;         // after two consecutive batches whose sample said "list every page", the next n batches of the same
@@ -104,10 +104,13 @@ int upload(scht_handle* h, const T* src, size_t count, const T** dst) {
 
 // Leaf-scan kernel variants: consumer warps per CTA x resident CTAs per SM the register budget is sized for.
 //   0: 8 warps (64 queries/tile), 1 CTA/SM   1: 7 warps (56 queries/tile, 256 threads with the producer), 2 CTAs/SM
-//   2: 4 warps (32 queries/tile), 3 CTAs/SM
-constexpr int kVariantWarps[3] = {8, 7, 4};
+//   2: 4 warps (32 queries/tile), 3 CTAs/SM   3: the same with 96 registers and a 2-stage ring, 4 CTAs/SM
+// auto: 2, and 3 for the SEED scan of narrow points with short lists (1.50 -> 1.41 ms on 1Mx16; no gain for wide points or
+// K = 100; the FP32-bound main scan keeps its 128 registers)
+constexpr int kVariantWarps[4] = {8, 7, 4, 4};
 int pick_variant(const scht_handle* h, int K) {
     int v = h->scan_variant;
+    if (v < 0) v = 2;  // auto (the seed scan of narrow points runs as variant 3, see run_batch)
     int nw = kVariantWarps[v];
     if ((int)scan_smem_bytes(nw, h->T.dpad, K) <= h->max_smem) return v;
     if ((int)scan_smem_bytes(4, h->T.dpad, K) <= h->max_smem) return 2;
@@ -129,6 +132,8 @@ int launch_scan(scht_handle* h, int variant, const ScanParams& P, cudaStream_t s
     switch (variant) {
         case 0: return full ? launch_scan_t<8, 1, true>(h, P, s) : launch_scan_t<8, 1, false>(h, P, s);
         case 1: return full ? launch_scan_t<7, 2, true>(h, P, s) : launch_scan_t<7, 2, false>(h, P, s);
+        case 3:  // 4 CTAs/SM (96 registers, 2-stage ring)
+            return full ? launch_scan_t<4, 4, true, 2>(h, P, s) : launch_scan_t<4, 4, false, 2>(h, P, s);
         default: {
             // three resident CTAs per SM are what hides the exact path's FP64 chains: when the query block of wide points makes a
             // 4-stage CTA too big for that (D >= 64), a 2-stage ring brings the third CTA back
@@ -246,7 +251,8 @@ int run_batch(scht_handle* h, const float* d_q, int nq, int K, bool brute, bool 
         // K4a seed scan of the approximate leaves
         P.mode = kScanSeed;
         P.write_mode = kWriteState;
-        int rc = launch_scan(h, variant, P, s);
+        const int seed_variant = (h->scan_variant < 0 && variant == 2 && T.dpad <= kRowsPerStage && K <= 32) ? 3 : variant;  // same 32-query tiles
+        int rc = launch_scan(h, seed_variant, P, s);
         if (rc) return rc;
         launches++;
         scans++;
@@ -581,7 +587,7 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     h->depth = depth;
     h->h_leaf_start.assign(t->leaf_start, t->leaf_start + L);
     h->h_leaf_count.assign(t->leaf_count, t->leaf_count + L);
-    if (const char* ev = getenv("SCHT_SCAN_VARIANT")) h->scan_variant = std::max(0, std::min(2, atoi(ev)));
+    if (const char* ev = getenv("SCHT_SCAN_VARIANT")) h->scan_variant = std::max(-1, std::min(3, atoi(ev)));
     auto fail_free = [&](int rc) {
         scht_destroy(h);
         return rc;

@@ -210,14 +210,14 @@ def test_prefilter_on_and_off(pkg, orc, monkeypatch, tc, n, dim, nq, K, pct, kin
     ix.close()
 
 
-@pytest.mark.parametrize("env", [{"SCHT_SCAN_VARIANT": "0"}, {"SCHT_SCAN_VARIANT": "1"}, {"SCHT_SCAN_VARIANT": "2"},
+@pytest.mark.parametrize("env", [{"SCHT_SCAN_VARIANT": "0"}, {"SCHT_SCAN_VARIANT": "1"}, {"SCHT_SCAN_VARIANT": "2"}, {"SCHT_SCAN_VARIANT": "3"}, {"SCHT_SCAN_STAGES": "2"}, {"SCHT_SCAN_STAGES": "4"},
                                  {"SCHT_TRAVERSE_SAMPLING": "0"}, {"SCHT_TRAVERSE_SAMPLING": "0", "SCHT_TC": "1"},
                                  {"SCHT_TC": "1", "SCHT_TC_SPLIT": "0"}, {"SCHT_TC": "1", "SCHT_TC_SPLIT": "3"},
                                  {"SCHT_TC": "1", "SCHT_TC_SPLIT": "8"}, {"SCHT_SEED_POINTS": "256"}, {"SCHT_SEED_POINTS": "8192"},
                                  {"SCHT_TC": "1", "SCHT_TC_N256": "1"}, {"SCHT_TC": "1", "SCHT_TC_N256": "0"},
                                  {"SCHT_TC": "1", "SCHT_TC_ISSUERS": "4"}, {"SCHT_TC": "1", "SCHT_TC_ISSUERS": "2", "SCHT_TC_N256": "0"}])
 def test_kernel_variants_and_knobs(pkg, orc, monkeypatch, env):
-    """every leaf-scan kernel variant (8/7/4 consumer warps), the traversal with sampling switched off, prefilter tiles
+    """every leaf-scan kernel variant (8/7/4 consumer warps, 2- and 4-stage rings), the traversal with sampling switched off, prefilter tiles
     split into page segments (partial lists merged), other seed-neighbourhood sizes and the MMA issue shapes (two or four
     issuers, half-page or whole-page chains; the test data has 16-D one-slice and 20-D two-slice pages) give the
     reference's bits (the knobs only change the schedule)"""
