@@ -237,6 +237,10 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
     const int tile = (int)blockIdx.x - seg * n_tiles;
     const int q_begin = tile * kTcQ;
     const int nq_tile = min(kTcQ, P.nq - q_begin);
+    // Tile slot (= TMEM lane = operand row) i holds the tile's query number ord(i) = 4 (i % 32) + i / 32 in bucket order: queries
+    // that are neighbours in bucket order (same approximate leaf, same cluster, hot on the same pages) are dealt round-robin to the
+    // four lane quadrants, so a burst of survivors is shared by all four rescorers instead of filling one quadrant's rings
+    auto ord = [](int slot) { return ((slot & 31) << 2) | (slot >> 5); };
     const float scale = TP.scale;
 
     // ---- set-up ---------------------------------------------------------------------------------------------
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
     }
     if (tid < 4 * kTcEpiWarps) q_tail[tid] = 0;  // ring counters, done flags, reservations (contiguous)
     for (int i = tid; i < kTcQ; i += blockDim.x) {
-        int qid = (i < nq_tile) ? P.q_order[q_begin + i] : -1;
+        int qid = (ord(i) < nq_tile) ? P.q_order[q_begin + ord(i)] : -1;
         qids[i] = qid;
         int a0 = 0, a1 = 0;
         if (qid >= 0) {
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
     }
     for (int i = tid; i < kTcQ * K; i += blockDim.x) {
         int qi = i / K;
-        lists[i] = (qi < nq_tile) ? P.state[(size_t)(q_begin + qi) * K + (i - qi * K)] : kEmptyKey;
+        lists[i] = (ord(qi) < nq_tile) ? P.state[(size_t)(q_begin + ord(qi)) * K + (i - qi * K)] : kEmptyKey;
     }
     for (int i = tid; i < kTcQ; i += blockDim.x) tq_s[i] = -3.0e38f;  // real bounds are published below, before the pipeline starts
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // sA was written through the generic proxy
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
         const bool is_epi = warp < kTcEpiWarps;
         const int quad = is_epi ? (warp & 3) : (warp - (kTcEpiWarps + 1 + N_ISS));
         const int qi = quad * 32 + lane;  // tile-local query
-        const bool valid_q = qi < nq_tile;
+        const bool valid_q = ord(qi) < nq_tile;
         float qn2 = 0.f, s1 = 0.f, l1 = 0.f, amax = 0.f;
         const float* my_qrow = P.q + (size_t)(valid_q ? qids[qi] : 0) * T.dim;
         for (int j = 0; j < T.dim; j++) {
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             // ---- results: the rescorer owns the lists of its 32 queries ----
             for (int qq = 0; qq < 32; qq++) {
                 const int ql = quad * 32 + qq;
-                if (ql >= nq_tile) break;
+                if (ord(ql) >= nq_tile) continue;
                 const uint64_t* L = lists + (size_t)ql * K;
                 const int qid = qids[ql];
                 if (TP.n_seg > 1) {  // a page segment of a split tile: partial lists, merged afterwards
@@ -589,7 +593,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                         if (P.dist_out) P.dist_out[(size_t)qid * K + k] = __fsqrt_rn(d2);
                     }
                 } else if (P.write_mode == kWriteState) {
-                    for (int k = lane; k < K; k += 32) P.state[(size_t)(q_begin + ql) * K + k] = L[k];
+                    for (int k = lane; k < K; k += 32) P.state[(size_t)(q_begin + ord(ql)) * K + k] = L[k];
                 } else {
                     for (int k = lane; k < K; k += 32) P.keys_out[(size_t)qid * K + k] = L[k];
                 }
@@ -701,7 +705,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             __threadfence_block();
             if (lane == 0) *reinterpret_cast<volatile int*>(q_done + warp) = 1;
             if (P.counters && half == 0 && sub == 0 && lane == 0) {
-                int nvalid = max(0, min(32, nq_tile - quad * 32));
+                int nvalid = max(0, min(32, (nq_tile - quad + 3) / 4));  // slots of the quadrant with ord(slot) < nq_tile
                 atomicAdd(&P.counters[0], n_pairs * (unsigned long long)nvalid);
             }
         }
