@@ -42,6 +42,9 @@ constexpr int kTcEpiWarps = 16;
 constexpr int kTcMaxMmaWarps = 4;  // MMA issuers: 2 (one per page parity; narrow points, one K slice per page) or 4 (one per TMEM buffer)
 __host__ __device__ constexpr int tc_threads(int n_iss) { return (kTcEpiWarps + 1 + n_iss + 4) * 32; }  // + producer, MMA issuers, 4 rescorers
 constexpr int kTcQueueCap = 256;   // ring entries per epilogue warp (power of two)
+#ifndef SCHT_RESCORER_SLEEP_NS
+#define SCHT_RESCORER_SLEEP_NS 4000  // an idle rescorer's pause between polls of its rings
+#endif
 
 struct TcScanParams {
     ScanParams S;            // q, q_order, q_leaf, nq, K, write_mode, pos range, ranges (tile = 128 queries), state, outputs
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                 }
                 if (total == 0) {
                     if (all_done) break;
-                    __nanosleep(4000);  // survivors are rare (~1 per 10 pages and warp): poll seldom, the pipeline warps need the issue slots
+                    __nanosleep(SCHT_RESCORER_SLEEP_NS);  // survivors are rare (~1 per 10 pages and warp): poll seldom, the pipeline warps need the issue slots
                     continue;
                 }
                 {
