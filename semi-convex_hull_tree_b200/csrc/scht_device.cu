@@ -658,9 +658,9 @@ extern "C" int scht_create(const scht_tree_desc* t, int device, scht_handle** ou
     {
         // seed neighbourhood of every leaf: the smallest enclosing subtree with >= kSeedPoints points
         std::vector<int> ss(L), se(L);
-        // (wide points: the seed scan's exact evaluations cost a 128-step FP64 chain each; one tree level less -- 512 points -- took
-        // the SIFT-like 1Mx128 step from 46.7 to 44.0 ms)
-        int seed_points = (dpad >= 64) ? kSeedPoints / 2 : kSeedPoints;
+        // (512 points, about one tree level above a 500-point leaf.  Against 1024: 1Mx16 step 11.41 -> 11.29 ms, Gaussian clusters
+        // 2Mx32 47.3 -> 46.2 ms, SIFT-like 1Mx128 46.7 -> 44.0 ms; 256: 11.21 ms on 1Mx16, 2048: 11.74 ms)
+        int seed_points = kSeedPoints;
         if (const char* ev = getenv("SCHT_SEED_POINTS")) seed_points = std::max(1, atoi(ev));
         for (int i = 0; i < nn; i++) {
             if (rec[i].leaf < 0) continue;

@@ -31,7 +31,7 @@ constexpr int kStages = 4;
 constexpr int kQPerWarp = 8;       // queries owned by one consumer warp
 constexpr int kMaxLevel = 32;      // constraints beyond this depth are ignored by the pruning bound (still valid)
 #ifndef SCHT_SEED_POINTS
-#define SCHT_SEED_POINTS 1024
+#define SCHT_SEED_POINTS 512
 #endif
 constexpr int kSeedPoints = SCHT_SEED_POINTS;  // size of the seed neighbourhood (positions) scanned before the traversal bounds are taken
 constexpr int kMaxCuts = 64;       // the traversal of one tile is split into <= 64 subtree jobs (one warp each)
