@@ -9,8 +9,14 @@ Default workload = BASELINE.json configs[1]: synthetic uniform 1M points x 16-D,
 
 value  : queries/s with the queries already resident in HBM (scht_query_device), CUDA events, max over ranks
 e2e    : queries/s through scht_query with pinned HOST buffers (H2D of the queries and D2H of idx+dist2 inside the timed region)
-roofline: leaf-scan kernel: algorithmic bytes (points the REFERENCE algorithm scans x D x 4 B) / measured scan-kernel time
-cpu_baseline: the reference (oracle/_ref/ref_knn, kind "reference") or the C oracle (kind "port") on a bounded query sample
+roofline: the dominant kernel (main leaf scan) against the roof that binds it: the tensor pipe when the tcgen05 prefilter
+         scan ran (issued MMA flops / measured bf16 peak), the FP32 pipe for the exact scan; the SURVEY 8d HBM form
+         (points the REFERENCE algorithm scans x D x 4 B / kernel time) is kept next to it as `hbm_algorithmic`
+cpu_baseline: the reference (oracle/_ref/ref_knn, kind "reference") or the C oracle (kind "port") on a bounded query sample;
+         the GPU's answers for the same queries are compared with it bit for bit (parity_checked / parity_mismatches)
+With WORLD_SIZE > 1 the line also carries `sharded_dataset` (one leaf shard per rank, NCCL all-reduce of the seed bounds +
+all-to-all of the K-lists, merged per query slice) and `single_process` (rank 0 alone drives all GPUs through
+scht_create_multi: strong scaling of one call, query-sharded and dataset-sharded).
 """
 import argparse
 import importlib
@@ -32,6 +38,8 @@ WORKLOADS = {
     # name: (n, dim, nq, K, pct, kind)
     "uniform_1Mx16_q100k_K10": (1_000_000, 16, 100_000, 10, 0.0005, "uniform"),
     "gauss_10Mx32_q1M_K10": (10_000_000, 32, 1_000_000, 10, 0.00005, "gauss1000"),
+    "gauss_10Mx32_q1M_K1": (10_000_000, 32, 1_000_000, 1, 0.00005, "gauss1000"),
+    "gauss_10Mx32_q1M_K100": (10_000_000, 32, 1_000_000, 100, 0.00005, "gauss1000"),
     "gauss_2Mx32_q200k_K10": (2_000_000, 32, 200_000, 10, 0.00025, "gauss1000"),
     "gauss_2Mx32_q200k_K100": (2_000_000, 32, 200_000, 100, 0.00025, "gauss1000"),
     "gauss_2Mx32_q200k_K1": (2_000_000, 32, 200_000, 1, 0.00025, "gauss1000"),
@@ -39,6 +47,7 @@ WORKLOADS = {
     "posture_like_78095x15_self_K10": (78_095, 15, 78_095, 10, 0.005, "posture"),
     "smoke_50kx16_q4k_K10": (50_000, 16, 4_096, 10, 0.005, "uniform"),
     "uniform_100Mx16_q100k_K10": (100_000_000, 16, 100_000, 10, 0.000005, "uniform"),  # cfg5's data set on one GPU (13 GB device image)
+    "uniform_100Mx16_q10M_K10": (100_000_000, 16, 10_000_000, 10, 0.000005, "uniform"),  # cfg5 (use --single-process with --gpus N)
 }
 
 
@@ -108,13 +117,15 @@ class ClockSampler:
                 "power_w_max": max(pw), "reasons": reasons, "samples": len(rows), "samples_under_load": len(load)}
 
 
-def cpu_reference_sample(data, queries, K, pct, n_sample, cores):
-    """Times the reference CPU path on `n_sample` queries using `cores` host processes (the reference is
-    single-threaded: one process per core on disjoint query chunks).  Returns (q/s, kind, S_ref per query)."""
+def cpu_reference_sample(data, queries, K, pct, n_sample, cores, host_tree=None):
+    """Times the reference CPU path on the first `n_sample` queries using `cores` host processes (the reference is
+    single-threaded: one process per core on disjoint query chunks).  With `host_tree` (big data sets, where
+    every reference process would first spend minutes building the same tree) the C oracle port runs instead, OpenMP over
+    the sample on the given tree.  Returns dict(qps, kind, scanned_per_query, cores, idx, dist2)."""
     import oracle as orc
     n_sample = min(n_sample, len(queries))
     qs = np.ascontiguousarray(queries[:n_sample])
-    if orc.have_reference():
+    if host_tree is None and orc.have_reference():
         from io_formats import read_records, write_fmat
         with tempfile.TemporaryDirectory() as td:
             dp, qp = os.path.join(td, "d.fmat"), os.path.join(td, "q.fmat")
@@ -129,21 +140,31 @@ def cpu_reference_sample(data, queries, K, pct, n_sample, cores):
                 op = os.path.join(td, "o%d.knn" % c)
                 cmd = [orc.REF_BIN, "knn", dp, repr(float(pct)), "1", qp, str(K), "2", str(edges[c]), str(edges[c + 1]), op]
                 procs.append((subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL), op, edges[c + 1] - edges[c]))
-            secs, dists, hyper = [], 0, 0
+            secs, dists, idx, d2 = [], 0, [], []
             for p, op, m in procs:
                 if p.wait() != 0:
                     raise RuntimeError("ref_knn failed")
                 r = read_records(op)
                 secs.append(float(r["seconds"][1]))
                 dists += int(r["counters"][0])
-        return n_sample / max(secs), "reference", dists / n_sample, len(procs)
+                idx.append(r["idx"].reshape(m, K))
+                d2.append(r["dist2"].reshape(m, K))
+        return dict(qps=n_sample / max(secs), kind="reference", scanned_per_query=dists / n_sample, cores=len(procs),
+                    idx=np.concatenate(idx), dist2=np.concatenate(d2))
     # port: the C oracle with OpenMP over the same sample
     pkg = importlib.import_module("semi-convex_hull_tree_b200")
-    ht = pkg.HostTree(data, pct, 1)
+    ht = host_tree if host_tree is not None else pkg.HostTree(data, pct, 1)
     t0 = time.perf_counter()
-    _, _, _, _, cnt = orc.knn(ht, qs, K, alg=2, threads=cores)
+    idx, d2, _, _, cnt = orc.knn(ht, qs, K, alg=2, threads=cores)
     dt = time.perf_counter() - t0
-    return n_sample / dt, "port", int(cnt[0]) / n_sample, cores
+    return dict(qps=n_sample / dt, kind="port", scanned_per_query=int(cnt[0]) / n_sample, cores=cores, idx=idx, dist2=d2)
+
+
+def parity(gpu_idx, gpu_d2, cpu):
+    """bit-for-bit comparison of the GPU's answers with the CPU leg's on the same queries"""
+    m = len(cpu["idx"])
+    bad = int((gpu_idx[:m] != cpu["idx"]).any(axis=1).sum() + (gpu_d2[:m].view(np.uint32) != cpu["dist2"].view(np.uint32)).any(axis=1).sum())
+    return m, bad
 
 
 def main():
@@ -155,6 +176,10 @@ def main():
     ap.add_argument("--workload", default="uniform_1Mx16_q100k_K10", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU baseline sample (0 = auto: ~20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="one process drives --gpus N devices through scht_create_multi (no torchrun): strong scaling of one call")
+    ap.add_argument("--mode", default="both", choices=["queries", "dataset", "both"], help="--single-process: sharding mode(s) to time")
+    ap.add_argument("--no-multi-extras", action="store_true", help="WORLD_SIZE > 1: skip the sharded_dataset / single_process records")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -173,18 +198,21 @@ def main():
         vals = []
         for s in range(args.warmup + args.steps):
             off = (s * per_step) % max(1, nq - per_step + 1)
-            v, knd, s_ref, used = cpu_reference_sample(data, queries[off:off + per_step], K, pct, per_step, cores)
+            r = cpu_reference_sample(data, queries[off:off + per_step], K, pct, per_step, cores)
             if s >= args.warmup:
-                vals.append(v)
+                vals.append(r["qps"])
         v = float(np.mean(vals))
         line = {"impl": "reference", "metric": "exact k-NN queries/sec (K=%d)" % K, "value": v, "unit": "queries/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step / v, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": v, "unit": "queries/s", "cores": used, "kind": knd,
+                "cpu_baseline": {"value": v, "unit": "queries/s", "cores": r["cores"], "kind": r["kind"], "queries_per_s_per_core": v / r["cores"],
                                  "sample": "%d queries per step, one single-threaded reference process per core" % per_step},
                 "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return 0
+
+    if args.single_process:
+        return single_process_main(args, config)
 
     import torch
     import torch.distributed as dist
@@ -194,18 +222,23 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    data, queries = make_data(kind, n, dim, nq, 1234)
+    data, queries0 = make_data(kind, n, dim, nq, 1234)
+    queries = queries0
     if world > 1:  # weak scaling: every rank gets its own 100k queries, the tree is replicated
-        _, queries = make_data(kind, 1, dim, nq, 1234 + 17 * rank) if kind == "uniform" else (None, queries[np.random.default_rng(rank).permutation(nq)])
+        _, queries = make_data(kind, 1, dim, nq, 1234 + 17 * rank) if kind == "uniform" else (None, queries0[np.random.default_rng(rank).permutation(nq)])
     # the tree: built on this rank's GPU by scht_build_tree_device (bit-identical to the host builder, tests/test_gpu_build.py)
     t0 = time.perf_counter()
     ht = pkg.HostTree(data, pct, 1, device=local_rank)
     t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
     ix = pkg.Index(ht, device=local_rank)
+    t_create = time.perf_counter() - t0
     info = ix.info()
+    lay = ix.layout()
     arr = ht.arrays()
-    config.update({"n_leaves": int(arr["n_leaves"]), "tree_depth": int(arr["depth"]), "device_build_s": round(t_build, 2),
-                   "device_tree_MB": info["device_bytes"] >> 20})
+    tree_info = {"n_leaves": int(arr["n_leaves"]), "tree_depth": int(arr["depth"]), "device_build_s": round(t_build, 2),
+                 "device_create_s": round(t_create, 2), "device_tree_MB": info["device_bytes"] >> 20, "scan_groups": lay["scan_groups"],
+                 "scan_pages": lay["scan_pages"]}
 
     # device-resident leg
     dq = torch.from_numpy(queries).to(dev)
@@ -259,6 +292,13 @@ def main():
         t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1]) / 1e3
+
+    extras = {}
+    if world > 1 and not args.no_multi_extras:
+        try:
+            extras = multi_gpu_extras(pkg, dist, torch, ht, ix, queries0, dim, K, rank, local_rank, world, dev, min(args.steps, 3))
+        except Exception as ex:  # never lose the headline line because an extra failed
+            extras = {"multi_gpu_extras_error": repr(ex)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -268,22 +308,29 @@ def main():
     e2e = world * nq * args.steps / e2e_s
     line = {"metric": "exact k-NN queries/sec (K=%d)" % K, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config,
+            "dtype": "f32", "data": "synthetic", "config": config, "tree": tree_info,
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * K * 8},
             "gpu_launches": int(stats["kernel_launches"]) * args.steps, "clocks": sampler.summary()}
+    line.update(extras)
 
-    # CPU baseline + the reference algorithm's scan volume (algorithmic bytes of the roofline)
+    # CPU baseline (+ parity of the GPU's answers on the same queries) and the reference algorithm's scan volume
     s_ref = None
-    if n > 10_000_000:
-        args.no_cpu_baseline = True  # the reference's single-threaded host build alone would take hours at this size
+    exit_code = 0
     if not args.no_cpu_baseline:
         try:
+            big = n * dim > 64_000_000  # every reference process would rebuild the tree for minutes: run the C oracle port on the device-built tree
             guess_qps_core = 30.0 * (1_000_000 * 16) / (n * dim)
-            n_sample = args.cpu_sample or int(max(cores, min(nq, 20.0 * guess_qps_core * cores)))
-            v, knd, dists_per_q, used = cpu_reference_sample(data, queries, K, pct, n_sample, cores)
-            s_ref = dists_per_q
-            line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": used, "kind": knd,
-                                    "sample": "first %d queries of the step, one single-threaded reference process per core" % n_sample}
+            n_sample = args.cpu_sample or int(max(cores, min(nq, (6.0 if big else 20.0) * guess_qps_core * cores)))
+            r = cpu_reference_sample(data, queries, K, pct, n_sample, cores, host_tree=ht if big else None)
+            s_ref = r["scanned_per_query"]
+            line["cpu_baseline"] = {"value": r["qps"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"],
+                                    "queries_per_s_per_core": r["qps"] / r["cores"],
+                                    "sample": "first %d queries of the step, %s" % (n_sample, "one single-threaded reference process per core"
+                                                                                    if r["kind"] == "reference" else "C oracle port, OpenMP over the sample")}
+            checked, bad = parity(hidx.numpy(), hd2.numpy(), r)
+            line["parity_checked"], line["parity_mismatches"] = checked, bad
+            if bad:
+                exit_code = 1
         except Exception as ex:  # never lose the GPU line because the CPU leg failed
             line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": cores, "kind": "port", "sample": "failed: %r" % (ex,)}
     peaks = {}
@@ -294,49 +341,200 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     tpeak = float(peaks.get("bf16_tflops", 1590.0))
     s_gpu = stats["dist_computations"] / max(1, stats["n_queries"])
-    if s_ref is None:
-        s_ref = s_gpu
     used_tc = stats["prefilter_batches"] > 0
     # dominant kernel = the main leaf scan (k_scan_tc with the tensor-core prefilter, else k_scan); one launch per step
     main_s = stats["ms_main_scan"] / 1e3
-    alg_bytes = s_ref * dim * 4 * nq  # points the REFERENCE algorithm scans x D x 4 B, for the queries of one step
-    achieved = alg_bytes / main_s / 1e9
     clk = (line["clocks"].get("sm_mhz") or 1965) * 1e6
     pairs = stats["dist_computations"]
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from the committed ncu --set full capture
+    prof = {}  # numbers of the committed ncu --set full capture of this workload's dominant kernel (profiles/traffic.json)
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = tj.get(args.workload, {}).get("k_scan_tc" if used_tc else "k_scan")
-        if ent:
-            traffic = ent["dram_bytes_per_launch"]
+        prof = tj.get(args.workload, {}).get("k_scan_tc" if used_tc else "k_scan") or {}
     except Exception:
         pass
-    line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
-                        "kernel": "k_scan_tc (main scan, tensor-core prefilter + exact rescoring)" if used_tc else "k_scan (main scan)",
-                        "kernel_ms": stats["ms_main_scan"], "launches_per_step": 1,
-                        "algorithmic_bytes_per_launch": alg_bytes, "ref_scanned_points_per_query": s_ref, "gpu_scanned_points_per_query": s_gpu,
-                        "note": "algorithmic bytes per SURVEY 8d (reference-scanned points x D x 4 B). Every staged page is reused by all "
-                                "queries of a tile and re-read from L2 by the other tiles, so DRAM traffic is far below the algorithmic "
-                                "bytes and frac >> 1: the kernel is not HBM-bound (see `tensor` / `fp32` below and DESIGN.md 5)",
-                        "other_kernels_ms": {"seed_scan": stats["ms_seed_scan"], "traverse": stats["ms_traverse"],
-                                             "rest": stats["ms_device"] - stats["ms_seed_scan"] - stats["ms_traverse"] - stats["ms_main_scan"]}}
+    kp = (dim + 3 + 15) // 16 * 16
     if used_tc:
-        kp = (dim + 3 + 15) // 16 * 16
-        line["roofline"]["tensor"] = {"achieved_tflops_algorithmic": pairs * dim * 2 / main_s / 1e12,
-                                      "achieved_tflops_issued": pairs * kp * 2 / main_s / 1e12, "peak_tflops": tpeak,
-                                      "frac_issued": pairs * kp * 2 / main_s / 1e12 / tpeak,
-                                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; FP16 and BF16 MMA run at the same rate)",
-                                      "note": "tensor pipe ~30 % busy (ncu): the epilogue (one TMEM read + one min per pair, ALU pipe ~60 % "
-                                              "busy) and the MMA->epilogue hand-off latency bound the kernel, not the tensor pipe"}
+        ach = pairs * kp * 2 / main_s / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; FP16 and BF16 MMA run at the same rate)" if peaks else "fallback 1590 TFLOP/s",
+                "kernel": "k_scan_tc (main scan: tcgen05 FP16 prefilter + exact rescoring)",
+                "flops": "issued: (query, point) pairs the kernel put through the MMA x K'=%d x 2; algorithmic 2*D flops = %.1f TFLOP/s" % (
+                    kp, pairs * dim * 2 / main_s / 1e12)}
     else:
-        line["roofline"]["fp32"] = {"lane_ops_per_s": pairs * dim * 2 / main_s,
-                                    "frac_of_128_lanes_per_clk_per_sm": pairs * dim * 2 / main_s / (148 * 128 * clk)}
+        ach = pairs * dim * 2 / main_s / 1e12
+        fpeak = 148 * 128 * 2 * clk / 1e12
+        roof = {"bound": "fp32", "achieved": ach, "peak": fpeak, "unit": "TFLOP/s", "frac": ach / fpeak,
+                "peak_source": "148 SMs x 128 FP32 lanes x 2 flop x measured SM clock (FADD2+FFMA2 per dimension: 2 lane-ops per pair and dimension)",
+                "kernel": "k_scan (main scan, exact FP32)"}
+    roof.update({"traffic": prof.get("dram_bytes_per_launch"), "kernel_ms": stats["ms_main_scan"], "launches_per_step": 1,
+                 "gpu_scanned_points_per_query": s_gpu, "ref_scanned_points_per_query": s_ref,
+                 "ncu": {k: prof[k] for k in ("tensor_pipe_pct", "alu_pipe_pct", "l2_hit_pct", "capture") if k in prof} or None,
+                 "other_kernels_ms": {"seed_scan": stats["ms_seed_scan"], "select_or_traverse": stats["ms_traverse"],
+                                      "rest": stats["ms_device"] - stats["ms_seed_scan"] - stats["ms_traverse"] - stats["ms_main_scan"]}})
+    if s_ref is not None:
+        alg_bytes = s_ref * dim * 4 * nq  # points the REFERENCE algorithm scans x D x 4 B, for the queries of one step
+        roof["hbm_algorithmic"] = {"achieved": alg_bytes / main_s / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / main_s / 1e9 / peak,
+                                   "algorithmic_bytes_per_launch": alg_bytes, "measured_dram_bytes_per_launch": prof.get("dram_bytes_per_launch"),
+                                   "note": "SURVEY 8d form. Every staged page is shared by the 128 queries of a tile and the images stay in L2, "
+                                           "so DRAM moves orders of magnitude fewer bytes and this fraction exceeds 1: HBM does not bind the kernel"}
+    line["roofline"] = roof
     line["stats_one_step"] = stats
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return exit_code
+
+
+def multi_gpu_extras(pkg, dist, torch, ht, ix, queries0, dim, K, rank, local_rank, world, dev, steps):
+    """WORLD_SIZE > 1 only.  (1) sharded-dataset mode, one process per GPU: rank r holds the leaves of shard r
+    (scht_create_shard), every rank scans its shard for ALL queries; the seed bounds are all-reduced (MIN) and the K-lists
+    exchanged with ONE all-to-all, both NCCL over NVLink; rank r merges its query slice.  (2) rank 0 alone drives all GPUs
+    through scht_create_multi (the other ranks wait on the host): strong scaling of one call."""
+    sh = importlib.import_module("semi-convex_hull_tree_b200.sharding")
+    out = {}
+    nq = len(queries0)
+    stream = torch.cuda.current_stream().cuda_stream
+    parts = sh.leaf_shards(ht.arrays()["leaf_count"], world)
+    shard = pkg.Index(ht, device=local_rank, leaf_range=parts[rank])
+    dq = torch.from_numpy(queries0).to(dev)
+    bound = torch.empty(nq, dtype=torch.float32, device=dev)
+    keys = torch.empty((nq, K), dtype=torch.int64, device=dev)
+    qb, qe = sh.query_shard(nq, world, rank)
+    idx = torch.empty((qe - qb, K), dtype=torch.int32, device=dev)
+    d2 = torch.empty((qe - qb, K), dtype=torch.float32, device=dev)
+    a2a = sh.torch_all_to_all()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step(timed=False):
+        shard.partial_seed_device(dq.data_ptr(), nq, dim, K, bound.data_ptr(), stream)
+        dist.all_reduce(bound, op=dist.ReduceOp.MIN)
+        shard.partial_scan_device(dq.data_ptr(), nq, dim, K, bound.data_ptr(), keys.data_ptr(), stream)
+        if timed:
+            ev[2].record()
+        recv, _ = sh.exchange_partial_keys(keys, world, rank, a2a)
+        if timed:
+            ev[3].record()
+        stacked = torch.stack(recv).contiguous()  # [world][nq_mine][K]
+        shard.merge_partial_device(stacked.data_ptr(), world, qe - qb, dim, K, idx.data_ptr(), d2.data_ptr(), None, stream)
+
+    step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(steps):
+        step()
+    ev[1].record()
+    torch.cuda.synchronize()
+    step(timed=True)
+    torch.cuda.synchronize()
+    t = torch.tensor([ev[0].elapsed_time(ev[1]) / steps, ev[2].elapsed_time(ev[3])], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # the same query slice through the replicated tree of this rank
+    ridx, rd2 = torch.empty_like(idx), torch.empty_like(d2)
+    ix.query_device(dq[qb:qe].contiguous().data_ptr(), qe - qb, dim, K, ridx.data_ptr(), rd2.data_ptr(), None, stream)
+    torch.cuda.synchronize()
+    ok = torch.tensor([int(torch.equal(ridx, idx) and torch.equal(rd2.view(torch.int32), d2.view(torch.int32)))], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    a2a_bytes = nq * K * 8 * (world - 1) // world
+    out["sharded_dataset"] = {"mode": "one process per GPU, leaf shards, NCCL all-reduce(min) of seed bounds + all-to-all of K-lists", "n_gpus": world,
+                              "queries": nq, "ms_per_step": float(t[0]), "queries_per_s": nq / (float(t[0]) / 1e3),
+                              "all_to_all_bytes_per_rank": a2a_bytes, "all_to_all_ms": float(t[1]),
+                              "all_to_all_GBps_per_rank": a2a_bytes / max(float(t[1]), 1e-6) / 1e6,
+                              "shard_points": int(ht.arrays()["leaf_count"][parts[rank][0]:parts[rank][1]].sum()),
+                              "bit_identical_to_replicated_query": bool(ok.item())}
+    shard.close()
+    del dq, keys, bound
+    torch.cuda.synchronize()
+
+    # (2) single process, all GPUs: the other ranks wait on the host (a NCCL barrier would spin on their GPUs)
+    store = dist.distributed_c10d._get_default_store()
+    if rank == 0:
+        try:
+            if pkg.lib().scht_device_count() >= world:
+                big_q = np.concatenate([queries0] + [queries0[np.random.default_rng(g).permutation(nq)] for g in range(1, world)])
+                out["single_process"] = single_process_runs(pkg, torch, ht, big_q, dim, K, list(range(world)), steps, ("queries", "dataset"), single=ix)
+            else:
+                out["single_process"] = {"skipped": "only %d device(s) visible to rank 0" % pkg.lib().scht_device_count()}
+        finally:
+            store.set("scht_single_process_done", "1")
+    else:
+        store.wait(["scht_single_process_done"])
+    return out
+
+
+def single_process_runs(pkg, torch, ht, queries, dim, K, devices, steps, modes, single=None):
+    """one host process, scht_create_multi over `devices`: end-to-end q/s of one scht_query call with pinned host buffers"""
+    nq = len(queries)
+    hq = torch.from_numpy(queries).pin_memory()
+    res = {"n_gpus": len(devices), "queries_per_call": nq, "timing": "wall clock around scht_query (pinned host buffers in and out)"}
+    ref_idx = None
+    if single is not None:  # one GPU, same call: the strong-scaling denominator
+        hi, hd = torch.empty((nq, K), dtype=torch.int32).pin_memory(), torch.empty((nq, K), dtype=torch.float32).pin_memory()
+        single.query_raw(hq.data_ptr(), nq, dim, K, hi.data_ptr(), hd.data_ptr())
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            single.query_raw(hq.data_ptr(), nq, dim, K, hi.data_ptr(), hd.data_ptr())
+        dt = (time.perf_counter() - t0) / steps
+        res["one_gpu"] = {"ms_per_call": dt * 1e3, "queries_per_s": nq / dt}
+        ref_idx, ref_d2 = hi.clone(), hd.clone()
+    for mode in modes:
+        t0 = time.perf_counter()
+        mx = pkg.Index(ht, devices=devices, mode=pkg.SHARD_QUERIES if mode == "queries" else pkg.SHARD_DATASET)
+        t_create = time.perf_counter() - t0
+        hi, hd = torch.empty((nq, K), dtype=torch.int32).pin_memory(), torch.empty((nq, K), dtype=torch.float32).pin_memory()
+        mx.query_raw(hq.data_ptr(), nq, dim, K, hi.data_ptr(), hd.data_ptr())
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            mx.query_raw(hq.data_ptr(), nq, dim, K, hi.data_ptr(), hd.data_ptr())
+        dt = (time.perf_counter() - t0) / steps
+        ent = {"ms_per_call": dt * 1e3, "queries_per_s": nq / dt, "create_s": round(t_create, 2), "device_MB_total": mx.info()["device_bytes"] >> 20}
+        if ref_idx is not None:
+            ent["bit_identical_to_one_gpu"] = bool(torch.equal(hi, ref_idx) and torch.equal(hd.view(torch.int32), ref_d2.view(torch.int32)))
+            ent["speedup_vs_one_gpu"] = res["one_gpu"]["ms_per_call"] / (dt * 1e3)
+        else:
+            ref_idx, ref_d2 = hi.clone(), hd.clone()
+        res["query_sharded" if mode == "queries" else "dataset_sharded"] = ent
+        mx.close()
+    return res
+
+
+def single_process_main(args, config):
+    """python bench.py --single-process --gpus N [--workload ...]: one process, N GPUs behind one handle (cfg5: 100M x 16, 10M queries)"""
+    import torch
+    pkg = importlib.import_module("semi-convex_hull_tree_b200")
+    import oracle as orc
+    n, dim, nq, K, pct, kind = WORKLOADS[args.workload]
+    data, queries = make_data(kind, n, dim, nq, 1234)
+    t0 = time.perf_counter()
+    ht = pkg.HostTree(data, pct, 1, device=0)
+    t_build = time.perf_counter() - t0
+    modes = ("queries", "dataset") if args.mode == "both" else (args.mode,)
+    sampler = ClockSampler(0)
+    sampler.start()
+    res = single_process_runs(pkg, torch, ht, queries, dim, K, list(range(args.gpus)), args.steps, modes)
+    sampler.stop()
+    best = max(v["queries_per_s"] for k, v in res.items() if isinstance(v, dict) and "queries_per_s" in v)
+    config = dict(config, parallelism="one process, %d GPUs behind one handle (scht_create_multi)" % args.gpus)
+    line = {"metric": "exact k-NN queries/sec (K=%d)" % K, "value": best, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": 1,
+            "ms_per_step": 1e3 * nq / best, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config, "tree": {"n_leaves": int(ht.arrays()["n_leaves"]), "device_build_s": round(t_build, 2)},
+            "e2e": {"value": best, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * K * 8},
+            "single_process": res, "clocks": sampler.summary()}
+    # parity of a query sample against the C oracle on the same tree
+    if not args.no_cpu_baseline:
+        m = args.cpu_sample or 64
+        mx = pkg.Index(ht, devices=list(range(args.gpus)), mode=pkg.SHARD_DATASET if "dataset" in modes else pkg.SHARD_QUERIES)
+        gi, gd = mx.query(queries[:m], K)
+        mx.close()
+        t0 = time.perf_counter()
+        oi, od2, _, _, cnt = orc.knn(ht, queries[:m], K, alg=2)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": m / dt, "unit": "queries/s", "cores": min(os.cpu_count() or 1, 64), "kind": "port",
+                                "sample": "first %d queries, C oracle port (OpenMP) on the device-built tree" % m}
+        line["parity_checked"], line["parity_mismatches"] = parity(gi, gd, dict(idx=oi, dist2=od2))
+    print(json.dumps(line))
+    return 1 if line.get("parity_mismatches") else 0
 
 
 if __name__ == "__main__":

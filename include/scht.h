@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SCHT_ABI_VERSION 1
+#define SCHT_ABI_VERSION 2
 /* K limit of the device path. The reference's OpenCL path hard-codes MAX_NN_NUM=100
  * (Code/GPU_Convex_Tree.h:466, kernels/do_kNN_gpu.cl:360-362) without checking; we check. */
 #define SCHT_MAX_K 128
@@ -36,7 +36,8 @@ typedef enum scht_status {
     SCHT_ERR_NO_DEVICE = -3,    /* no CUDA device / not sm_100: the product has no CPU fallback */
     SCHT_ERR_CUDA = -4,         /* a CUDA runtime call or kernel failed; see scht_last_error() */
     SCHT_ERR_OOM = -5,          /* host or device allocation failed */
-    SCHT_ERR_DEGENERATE = -6,   /* tree build: unsplittable node (more than leaf-threshold identical rows) */
+    SCHT_ERR_DEGENERATE = -6,   /* reserved (the builders close an unsplittable node -- more than leaf-threshold identical rows -- as an
+                                   oversized leaf and return SCHT_OK, where the reference would recurse forever, Code/Convex_Tree.h:809-856) */
     SCHT_ERR_INTERNAL = -7
 } scht_status;
 
@@ -72,7 +73,8 @@ typedef struct scht_tree_desc {
 
     const int32_t* node_left;       /* [n_nodes] ConvexNode::left  (-1 for leaves) */
     const int32_t* node_right;      /* [n_nodes] ConvexNode::right (-1 for leaves) */
-    const int32_t* node_parent;     /* [n_nodes] ConvexNode::parent_index (-1 for root) */
+    const int32_t* node_parent;     /* [n_nodes] ConvexNode::parent_index (-1 for root); informational: scht_create derives the parents
+                                       from the validated child links and never reads this array (may be NULL) */
     const int32_t* node_leaf_index; /* [n_nodes] leaf id, -1 for internal nodes */
 
     const float* node_left_center;  /* [n_nodes*D] ConvexNode::left_center  (zeros for leaves) */
@@ -143,9 +145,37 @@ typedef struct scht_stats {
     double ms_main_scan;         /* CUDA-event time of the main scan (k_scan or k_scan_tc) */
 } scht_stats;
 
-/* Uploads the tree to `device` (CUDA ordinal) in the device layout described in DESIGN.md. */
+/* Uploads the tree to `device` (CUDA ordinal) in the device layout described in DESIGN.md.
+ * device == -1: every visible device, queries sharded (== scht_create_multi(tree, NULL, 0, SCHT_SHARD_QUERIES, out)). */
 int scht_create(const scht_tree_desc* tree, int device, scht_handle** out);
 void scht_destroy(scht_handle* h);
+
+/* ---- several GPUs behind one handle (the reference drives a single device, Code/GPU_Convex_Tree.h:443-446) ----
+ * One process, one host thread per GPU inside scht_query / scht_brute_force; the caller sees the same entry points and
+ * the same bits as with one GPU.
+ *   SCHT_SHARD_QUERIES  tree replicated on every device, each answers a contiguous slice of the queries of a call; the
+ *                       devices never communicate.
+ *   SCHT_SHARD_DATASET  each device holds a contiguous range of leaves (1/n of the points; the tree top is replicated) and
+ *                       scans it for all queries; seed bounds are read from the peers and every device's scan kernel stores
+ *                       its per-query K-lists directly into the memory of the device that owns the query (peer access over
+ *                       NVLink), which merges them.  Needs peer access between all listed devices.
+ * devices == NULL or n_devices <= 0: every visible device.  At most 16 devices. */
+#define SCHT_SHARD_QUERIES 0
+#define SCHT_SHARD_DATASET 1
+int scht_create_multi(const scht_tree_desc* tree, const int32_t* devices, int32_t n_devices, int32_t mode, scht_handle** out);
+
+/* A handle that holds only the leaves [leaf_begin, leaf_end) of the tree on `device` (the building block of the
+ * sharded-dataset mode when every GPU belongs to a different process, see scht_partial_seed_device).  scht_query on
+ * such a handle answers with the nearest neighbours among the resident points only. */
+int scht_create_shard(const scht_tree_desc* tree, int device, int32_t leaf_begin, int32_t leaf_end, scht_handle** out);
+
+/* Schedule knobs of a handle (none changes a result bit).  The SCHT_* environment variables only provide
+ * the defaults read when the handle is created.  Names: "tc" (0 off / 1 always / 2 auto), "tc_split", "tc_issuers",
+ * "tc_n256", "scan_variant", "scan_stages", "traverse_sampling", "sample_reuse", "seed_points", "page_select",
+ * "brute_tc", "pipeline", "pipeline_split"; "groups" can only be read (fixed at creation).  Unknown name or value out
+ * of range -> SCHT_ERR_INVALID_ARG. */
+int scht_set_option(scht_handle* h, const char* name, int64_t value);
+int scht_get_option(const scht_handle* h, const char* name, int64_t* value);
 
 /* BATCH_SIZE_OF_QUERY_POINTS_PUSCH_TO_DEVICE (Code/Convex_Tree.h:352, set_batch_size
  * Code/GPU_Convex_Tree.h:197-204): queries are streamed through the device in batches of this
@@ -176,21 +206,38 @@ int scht_query_device(scht_handle* h, const float* d_queries, int64_t n_queries,
 int scht_brute_force(scht_handle* h, const float* queries, int64_t n_queries, int32_t dim, int32_t K,
                      int32_t* idx_out, float* dist2_out, float* dist_out, scht_stats* stats);
 
+/* scht_brute_force with device-resident queries and outputs (single-GPU handles), like scht_query_device. */
+int scht_brute_force_device(scht_handle* h, const float* d_queries, int64_t n_queries, int32_t dim, int32_t K,
+                            int32_t* d_idx_out, float* d_dist2_out, float* d_dist_out, void* cuda_stream,
+                            scht_stats* stats);
+
 /* Approximate-leaf descent only (do_find_approximate_nodes, Code/GPU_Convex_Tree.h:168-193):
  * leaf_out[i] = leaf index reached by query i. Host buffers. */
 int scht_find_approximate_leaves(scht_handle* h, const float* queries, int64_t n_queries, int32_t dim,
                                  int32_t* leaf_out);
 
-/* ---- sharded-dataset mode: one GPU scans only leaves [leaf_begin, leaf_end) ---------
- * scht_query_partial_device writes, per query, K sorted 64-bit keys
- *     key = (float_bits(dist2) << 32) | (is_not_approx_leaf << 31) | sorted_position
- * (FLT_MAX-keyed for empty slots) into d_keys_out [n_queries*K]; lists from different leaf ranges are
- * merged exactly by scht_merge_partial_device (n_lists lists laid out [n_lists][n_queries][K]), which
- * also maps positions back to original indices and writes the final idx/dist2/dist arrays.
- * The exchange between the two calls (NCCL all-to-all over NVLink) is done by the caller. */
+/* ---- sharded-dataset mode, one process per GPU ---------------------------------------------------------
+ * Each rank creates a shard handle (scht_create_shard) for its leaf range and, per batch of queries (all ranks pass the
+ * same queries; n_queries * max(K, dim) < 2^31):
+ *   1. scht_partial_seed_device   seed scan where the query's approximate leaf is resident; d_bound_out[i] = K-th squared
+ *                                 distance of query i's seed list (FLT_MAX when the list is not full / nothing resident)
+ *   2. the caller takes the element-wise MINIMUM of d_bound over the ranks (one all-reduce of 4 B per query)
+ *   3. scht_partial_scan_device   main scan of the shard with that bound; per query K sorted 64-bit keys
+ *                                     key = (float_bits(dist2) << 32) | (is_not_approx_leaf << 31) | sorted_position
+ *                                 (FLT_MAX-keyed for empty slots) into d_keys_out [n_queries*K]
+ *   4. the ranks exchange the key lists (NCCL all-to-all over NVLink; scht_comm_* below does 2.-5. inside the library)
+ *   5. scht_merge_partial_device  merges n_lists lists laid out [n_lists][n_queries][K], maps positions back to original
+ *                                 indices and writes the final idx / dist2 / dist arrays.
+ * scht_query_partial_device is the one-call form for a handle that holds MORE than the requested leaf range (e.g. the whole
+ * tree): the seed scan uses everything resident, its K-th distance bounds the scan, and only positions of
+ * [leaf_begin, leaf_end) enter the key lists (leaf_begin = leaf_end = -1: the resident range). */
 int scht_query_partial_device(scht_handle* h, const float* d_queries, int64_t n_queries, int32_t dim, int32_t K,
                               int32_t leaf_begin, int32_t leaf_end, uint64_t* d_keys_out, void* cuda_stream,
                               scht_stats* stats);
+int scht_partial_seed_device(scht_handle* h, const float* d_queries, int64_t n_queries, int32_t dim, int32_t K,
+                             float* d_bound_out, void* cuda_stream);
+int scht_partial_scan_device(scht_handle* h, const float* d_queries, int64_t n_queries, int32_t dim, int32_t K,
+                             const float* d_bound, uint64_t* d_keys_out, void* cuda_stream, scht_stats* stats);
 int scht_merge_partial_device(scht_handle* h, const uint64_t* d_keys, int32_t n_lists, const float* d_queries,
                               int64_t n_queries, int32_t dim, int32_t K, int32_t* d_idx_out, float* d_dist2_out,
                               float* d_dist_out, void* cuda_stream);
@@ -198,6 +245,10 @@ int scht_merge_partial_device(scht_handle* h, const uint64_t* d_keys, int32_t n_
 /* Tree facts of a handle (for logs: print_tree_info, Code/Convex_Tree.h:946-958). */
 int scht_handle_info(const scht_handle* h, int32_t* dim, int64_t* n_points, int32_t* n_nodes, int32_t* n_leaves,
                      int32_t* device, int64_t* device_bytes);
+/* Device layout facts: devices behind the handle, sharding mode, scan groups / scan pages of the prefilter image of the
+ * first device (0 when it was not built) and the leaves resident there.  Any pointer may be NULL. */
+int scht_handle_layout(const scht_handle* h, int32_t* n_devices, int32_t* mode, int32_t* n_scan_groups,
+                       int64_t* n_scan_pages, int32_t* leaf_begin, int32_t* leaf_end);
 
 /* ------------------------------------------------------------------------------------------------
  * Data-set files.  Replaces read_data / read_data_dim_size / get_dim / get_data

@@ -58,7 +58,11 @@ SYMBOLS = {
     "scht_host_tree_build_seconds": (C.c_double, [C.c_void_p]),
     "scht_host_tree_free": (None, [C.c_void_p]),
     "scht_create": (C.c_int, [C.POINTER(TreeDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    "scht_create_multi": (C.c_int, [C.POINTER(TreeDesc), i32p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "scht_create_shard": (C.c_int, [C.POINTER(TreeDesc), C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "scht_destroy": (None, [C.c_void_p]),
+    "scht_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "scht_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "scht_set_batch_size": (C.c_int, [C.c_void_p, C.c_int64]),
     "scht_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.POINTER(Stats)]),
@@ -66,12 +70,18 @@ SYMBOLS = {
                                     C.c_void_p, C.POINTER(Stats)]),
     "scht_brute_force": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(Stats)]),
+    "scht_brute_force_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.POINTER(Stats)]),
     "scht_find_approximate_leaves": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "scht_query_partial_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
+    "scht_partial_seed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "scht_partial_scan_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.POINTER(Stats)]),
     "scht_merge_partial_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scht_handle_info": (C.c_int, [C.c_void_p, i32p, C.POINTER(C.c_int64), i32p, i32p, i32p, C.POINTER(C.c_int64)]),
+    "scht_handle_layout": (C.c_int, [C.c_void_p, i32p, i32p, i32p, C.POINTER(C.c_int64), i32p, i32p]),
     "scht_read_text": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(f32p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "scht_write_text": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
     "scht_write_bin": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
@@ -197,10 +207,18 @@ def desc_from_arrays(t):
     return d, keep
 
 
-class Index:
-    """Device-resident tree + query entry points (scht_create / scht_query ...)."""
+SHARD_QUERIES, SHARD_DATASET = 0, 1
 
-    def __init__(self, tree, device=0):
+
+class Index:
+    """Device-resident tree + query entry points (scht_create / scht_query ...).
+
+    device=i            one GPU (scht_create)
+    devices=[...]       several GPUs behind one handle (scht_create_multi; devices=[] = every visible device),
+                        mode = SHARD_QUERIES or SHARD_DATASET
+    leaf_range=(b, e)   only the leaves [b, e) on `device` (scht_create_shard)"""
+
+    def __init__(self, tree, device=0, devices=None, mode=SHARD_QUERIES, leaf_range=None, options=None):
         self._h = C.c_void_p()
         if isinstance(tree, HostTree):
             desc = tree.desc
@@ -210,8 +228,31 @@ class Index:
             desc = C.pointer(d)
         self.dim = desc.contents.dim
         self.n_points = desc.contents.n_points
-        _check(lib().scht_create(desc, int(device), C.byref(self._h)))
+        if devices is not None:
+            arr = (C.c_int32 * max(1, len(devices)))(*devices)
+            _check(lib().scht_create_multi(desc, arr if len(devices) else None, len(devices), int(mode), C.byref(self._h)))
+        elif leaf_range is not None:
+            _check(lib().scht_create_shard(desc, int(device), int(leaf_range[0]), int(leaf_range[1]), C.byref(self._h)))
+        else:
+            _check(lib().scht_create(desc, int(device), C.byref(self._h)))
         self.device = device
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
+
+    def set_option(self, name, value):
+        """scht_set_option: schedule knobs ("tc", "tc_split", "page_select", ...); results never depend on them"""
+        _check(lib().scht_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_int64()
+        _check(lib().scht_get_option(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    def layout(self):
+        nd, mode, ng, lb, le = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        npg = C.c_int64()
+        _check(lib().scht_handle_layout(self._h, C.byref(nd), C.byref(mode), C.byref(ng), C.byref(npg), C.byref(lb), C.byref(le)))
+        return dict(n_devices=nd.value, mode=mode.value, scan_groups=ng.value, scan_pages=npg.value, leaf_begin=lb.value, leaf_end=le.value)
 
     def set_batch_size(self, n):
         _check(lib().scht_set_batch_size(self._h, int(n)))
@@ -249,6 +290,19 @@ class Index:
         """scht_query_device: all pointers are device pointers on this handle's GPU."""
         _check(lib().scht_query_device(self._h, q_ptr, nq, dim, K, idx_ptr, d2_ptr, dist_ptr, stream,
                                        C.byref(stats) if stats is not None else None))
+
+    def brute_force_device(self, q_ptr, nq, dim, K, idx_ptr, d2_ptr, dist_ptr=None, stream=None, stats=None):
+        _check(lib().scht_brute_force_device(self._h, q_ptr, nq, dim, K, idx_ptr, d2_ptr, dist_ptr, stream,
+                                             C.byref(stats) if stats is not None else None))
+
+    def partial_seed_device(self, q_ptr, nq, dim, K, bound_ptr, stream=None):
+        """phase 1 of the sharded-dataset mode: seed scan on this shard, bound[i] = K-th squared seed distance"""
+        _check(lib().scht_partial_seed_device(self._h, q_ptr, nq, dim, K, bound_ptr, stream))
+
+    def partial_scan_device(self, q_ptr, nq, dim, K, bound_ptr, keys_ptr, stream=None, stats=None):
+        """phase 2: main scan of this shard with the (all-reduced) bounds -> sorted key lists"""
+        _check(lib().scht_partial_scan_device(self._h, q_ptr, nq, dim, K, bound_ptr, keys_ptr, stream,
+                                              C.byref(stats) if stats is not None else None))
 
     def query_partial_device(self, q_ptr, nq, dim, K, leaf_begin, leaf_end, keys_ptr, stream=None, stats=None):
         _check(lib().scht_query_partial_device(self._h, q_ptr, nq, dim, K, leaf_begin, leaf_end, keys_ptr, stream,

@@ -23,51 +23,9 @@
 
 #include <type_traits>
 
+#include "scht_types.cuh"
+
 namespace scht {
-
-constexpr int kPage = 256;         // sorted points per page
-constexpr int kRowsPerStage = 16;  // dims per shared-memory stage (16 rows x 256 floats = 16 KB)
-constexpr int kStages = 4;
-constexpr int kQPerWarp = 8;       // queries owned by one consumer warp
-constexpr int kMaxLevel = 32;      // constraints beyond this depth are ignored by the pruning bound (still valid)
-#ifndef SCHT_SEED_POINTS
-#define SCHT_SEED_POINTS 512
-#endif
-constexpr int kSeedPoints = SCHT_SEED_POINTS;  // size of the seed neighbourhood (positions) scanned before the traversal bounds are taken
-constexpr int kMaxCuts = 64;       // the traversal of one tile is split into <= 64 subtree jobs (one warp each)
-constexpr int kJobRanges = 8;      // page ranges per (tile, subtree job); overflow coalesces gaps (scans more, stays exact)
-constexpr int kRangeCap = kMaxCuts * kJobRanges;  // range slots per tile
-constexpr uint64_t kEmptyKey = 0x7f7fffffffffffffull;  // FLT_MAX bits (INFINITE, Code/cyw_types.h:18) | all ones
-constexpr float kPadCoord = 3.0e38f;                    // coordinate of padded positions: d2 overflows to +inf
-
-struct __align__(32) NodeRec {
-    int size;      // nodes in the subtree (DFS pre-order: subtree = [id, id+size))
-    int depth;     // root = 0; the node has `depth` constraints
-    int beta_off;  // into node_beta
-    int pos0, pos1;  // sorted-position range covered by the subtree
-    int leaf;      // leaf index, -1 for internal nodes
-    int right;     // right child id (left child = id+1), -1 for leaves
-    int pad;
-};
-
-struct DevTree {
-    int dim, dpad, n_points, n_pages, n_nodes, n_leaves;
-    const float* pages;       // [n_pages][dpad][256]
-    const float* rows;        // [n_pages*256][dpad] the same values row-major when dpad > 16 (else null): an exact re-evaluation reads ONE point
-    const int* orig_idx;      // [n_pages*256], -1 on padded positions
-    const NodeRec* nodes;     // [n_nodes]
-    const float* node_beta;   // CSR by NodeRec::beta_off, root-side constraint first
-    const float* node_normal; // [n_nodes][dpad] the node's own (last) constraint normal, zero padded
-    const float* node_lc;     // [n_nodes][dpad] left centre
-    const float* node_rc;     // [n_nodes][dpad] right centre
-    const int* leaf_start;    // [n_leaves]
-    const int* leaf_count;    // [n_leaves]
-    const int* seed_start;    // [n_leaves] position range scanned first for a query whose approximate leaf this is: the
-    const int* seed_end;      // [n_leaves]   smallest enclosing subtree with >= kSeedPoints points (its own leaf at least)
-    float xnorm_max;          // max ||x||_2 over the data set (pruning margin)
-    int n_cuts, cut_depth;    // subtree roots the traversal is split at (pre-order), all at depth <= cut_depth
-    const int* cut_path;      // [n_cuts][cut_depth+1] root-side path of each cut node (node ids, -1 padded), cut node last
-};
 
 // ---------------------------------------------------------------------------------------------------------
 // small PTX helpers
@@ -161,25 +119,6 @@ __device__ __forceinline__ void prefetch_row(const float4* row, int dpad) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// page builder: row-major sorted points -> dim-major pages
-// ---------------------------------------------------------------------------------------------------------
-__global__ void k_build_pages(const float* __restrict__ rows, int64_t row0, int64_t nrows, int dim, int dpad, int64_t n_points,
-                              float* __restrict__ pages, float* __restrict__ rows_out) {
-    // one thread per (position, dim) of the pages touched by rows [row0, row0+nrows) rounded to pages
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = nrows * dpad;
-    if (i >= total) return;
-    int64_t r = i / dpad;
-    int j = (int)(i - r * dpad);
-    int64_t pos = row0 + r;
-    float v = (j < dim) ? ((pos < n_points) ? rows[r * dim + j] : kPadCoord) : 0.f;
-    int64_t page = pos / kPage;
-    int lane = (int)(pos - page * kPage);
-    pages[(page * dpad + j) * kPage + lane] = v;
-    if (rows_out) rows_out[pos * dpad + j] = v;
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // K1: approximate-leaf descent (replaces the host loop Code/GPU_Convex_Tree.h:168-193 == Code/CPU_Convex_Tree.h:181-197)
 // thread per query; the two centre distances use the reference arithmetic so the branch decisions are identical.
 // Also histograms the leaves (first step of the bucketing).
@@ -205,7 +144,7 @@ __global__ void k_descend(DevTree T, const float* __restrict__ q, int nq, int* _
         levels++;
     }
     q_leaf[i] = nr.leaf;
-    if (leaf_hist) atomicAdd(&leaf_hist[nr.leaf], 1);
+    if (leaf_hist) atomicAdd(&leaf_hist[T.leaf_rank[nr.leaf]], 1);  // bucket = rank of the leaf (leaves ordered by scan group)
     if (counters) atomicAdd(&counters[3], (unsigned long long)(2 * levels));
 }
 
@@ -245,11 +184,11 @@ __global__ void k_leaf_prefix_sum(int* __restrict__ hist, int n) {
 }
 
 // K3b: scatter query ids into their leaf bucket -> q_order (queries sharing an approximate leaf become neighbours,
-// so one tile's queries want the same pages).  Order inside a bucket is arbitrary; results do not depend on it.
-__global__ void k_scatter(const int* __restrict__ q_leaf, int nq, int* __restrict__ cursor, int* __restrict__ q_order) {
+// and leaves near the same scan group are neighbours too (DevTree::leaf_rank), so one tile's queries want the same pages).  Order inside a bucket is arbitrary; results do not depend on it.
+__global__ void k_scatter(const int* __restrict__ q_leaf, const int* __restrict__ leaf_rank, int nq, int* __restrict__ cursor, int* __restrict__ q_order) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
-    int slot = atomicAdd(&cursor[q_leaf[i]], 1);
+    int slot = atomicAdd(&cursor[leaf_rank[q_leaf[i]]], 1);
     q_order[slot] = i;
 }
 __global__ void k_iota(int* __restrict__ a, int n) {
@@ -279,20 +218,39 @@ struct ScanParams {
     int pos_lo, pos_hi;    // only positions in [pos_lo,pos_hi) may enter the lists (sharded-dataset mode)
     const int2* ranges;    // [n_tiles][kMaxCuts][kJobRanges] page ranges [x,y) (kScanList)
     const int* n_ranges;   // [n_tiles][kMaxCuts]
+    int range_groups;      // groups of kJobRanges ranges to walk per tile (traversal: T.n_cuts, page selection: kMaxCuts)
+    const float* ext_bound;  // [nq] by query id, or null: an upper bound of the K-th distance^2 known from elsewhere (seed scan of
+                           //   another shard, seed scan of the tree for the brute-force entry): pairs beyond it are never evaluated
     uint64_t* state;       // [nq][K] keys by sorted slot
     uint64_t* keys_out;    // [nq][K] keys by query id (kWriteKeys)
+    // kWriteKeys with n_slices > 0 (sharded-dataset mode inside one process): the K keys of query qid are stored straight into
+    // the gather buffer of the device that owns the query slice g (slice_lo[g] <= qid < slice_lo[g+1]) -- peer memory over
+    // NVLink -- at key_tab[g] + ((size_t)list * slice_len(g) + qid - slice_lo[g]) * K, so the exchange needs no separate copy
+    int n_slices, list;
+    uint64_t* key_tab[kMaxShards];
+    int slice_lo[kMaxShards + 1];
     int* idx_out;          // [nq][K]
     float* d2_out;         // [nq][K]
     float* dist_out;       // [nq][K] or NULL
     unsigned long long* counters;  // [0] scanned (query,point) pairs, [1] exact re-evaluations, [2] list insertions
 };
 
+__device__ __forceinline__ uint64_t* keys_dst(const ScanParams& P, int qid) {
+    if (P.n_slices <= 0) return P.keys_out + (size_t)qid * P.K;
+    int g = 0;
+    while (g + 1 < P.n_slices && qid >= P.slice_lo[g + 1]) g++;
+    return P.key_tab[g] + ((size_t)P.list * (size_t)(P.slice_lo[g + 1] - P.slice_lo[g]) + (size_t)(qid - P.slice_lo[g])) * P.K;
+}
+__device__ __forceinline__ float ext_thr_of(const ScanParams& P, int qid) {
+    return (P.ext_bound && qid >= 0) ? fminf(P.ext_bound[qid] * 1.000001f, 3.402823466e+38f) : 3.402823466e+38f;
+}
+
 __host__ __device__ inline size_t scan_smem_bytes(int n_cwarps, int dpad, int K, int stages = kStages) {
     size_t tq = (size_t)n_cwarps * kQPerWarp;
     size_t b = (size_t)stages * kRowsPerStage * kPage * 4;  // stages
     b += (size_t)dpad * tq * 4;                              // queries, dim-major
     b += tq * (size_t)K * 8;                                 // lists
-    b += tq * 8 + tq * 5 * 4 + 16;                           // seed ranges, a0, a1, s0, s1, qid, misc
+    b += tq * 8 + tq * 6 * 4 + 16;                           // seed ranges, a0, a1, s0, s1, qid, external bound, misc
     b += 2 * stages * 8 + 64;                                // barriers
     return b;
 }
@@ -421,7 +379,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
     int* s0s = a1s + TQ;   // seed neighbourhood of each query (a superset of its approximate leaf)
     int* s1s = s0s + TQ;
     int* qids = s1s + TQ;
-    int* misc = qids + TQ;  // [0] number of seed ranges
+    float* exts = reinterpret_cast<float*>(qids + TQ);  // external bound of each query (FLT_MAX without one), shared memory: only the slow path reads it
+    int* misc = reinterpret_cast<int*>(exts + TQ);  // [0] number of seed ranges
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc + 4);
     uint64_t* empty_bar = full_bar + STAGES;
 
@@ -441,6 +400,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
     for (int i = tid; i < TQ; i += blockDim.x) {
         int qid = (i < nq_tile) ? P.q_order[q_begin + i] : -1;
         qids[i] = qid;
+        exts[i] = ext_thr_of(P, qid);
         int a0 = 0, a1 = 0, s0 = 0, s1 = 0;
         if (qid >= 0 && P.mode != kScanAll) {
             int leaf = P.q_leaf[qid];
@@ -476,7 +436,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
     const int n_seed = misc[0];
     if (tid == 0) {
         misc[1] = 1;  // one range: every page (kScanAll; slot TQ-1 is free there: no seed ranges)
-        if (P.mode == kScanAll) seed_rg[TQ - 1] = make_int2(0, T.n_pages);
+        if (P.mode == kScanAll) seed_rg[TQ - 1] = make_int2(T.page_lo, T.page_hi);
     }
     __syncthreads();
     const int2* list;
@@ -491,7 +451,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
     } else {
         list = P.ranges + (size_t)tile * kRangeCap;
         cnt = P.n_ranges + (size_t)tile * kMaxCuts;
-        n_groups = T.n_cuts;
+        n_groups = P.range_groups;
         stride = kJobRanges;
         n_skip = n_seed;  // pages of the seed scan are already in the lists
     }
@@ -528,7 +488,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
 #pragma unroll
     for (int qi = 0; qi < kQPerWarp; qi++) {
         float kth = __uint_as_float((uint32_t)(my_lists[(size_t)qi * K + K - 1] >> 32));
-        thr[qi] = (qw0 + qi < nq_tile) ? fminf(kth * 1.000001f, 3.402823466e+38f) : -1.f;
+        thr[qi] = (qw0 + qi < nq_tile) ? fminf(fminf(kth * 1.000001f, 3.402823466e+38f), exts[qw0 + qi]) : -1.f;
     }
     const bool brute = (P.mode == kScanAll);
     // Narrow points (the whole page is ONE stage): the stage is handed back to the producer only after the page's exact
@@ -732,7 +692,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
                     } while (__any_sync(0xffffffffu, bits != 0));
                 }
                 float kth = __uint_as_float((uint32_t)(L[K - 1] >> 32));
-                new_thr[qi] = (qw0 + qi < nq_tile) ? fminf(kth * 1.000001f, 3.402823466e+38f) : -1.f;
+                new_thr[qi] = (qw0 + qi < nq_tile) ? fminf(fminf(kth * 1.000001f, 3.402823466e+38f), exts[qw0 + qi]) : -1.f;
             }
 #pragma unroll
             for (int qi = 0; qi < kQPerWarp; qi++) thr[qi] = new_thr[qi];
@@ -766,7 +726,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
         } else if (P.write_mode == kWriteState) {
             for (int k = lane; k < K; k += 32) P.state[(size_t)(q_begin + qw0 + qi) * K + k] = L[k];
         } else {
-            for (int k = lane; k < K; k += 32) P.keys_out[(size_t)qid * K + k] = L[k];
+            uint64_t* dst = keys_dst(P, qid);
+            for (int k = lane; k < K; k += 32) dst[k] = L[k];
         }
     }
     if (P.counters) {
@@ -797,6 +758,7 @@ struct TraverseParams {
     const int* q_leaf;
     int nq, K, tq;           // tq = queries per tile of the leaf-scan kernel (<= 32*QL)
     const uint64_t* state;   // [nq][K] keys after the seed scan
+    const float* ext_bound;  // [nq] by query id or null (ScanParams::ext_bound)
     int2* ranges;            // [n_tiles][kMaxCuts][kJobRanges]
     int* n_ranges;           // [n_tiles][kMaxCuts]
     int leaf_lo, leaf_hi;    // only leaves in [leaf_lo, leaf_hi) are emitted (sharded-dataset mode)
@@ -874,7 +836,9 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
             // rounding margin of the bound: |error| <= c * D * 2^-24 * (||q|| + max||x||), see DESIGN.md
             absm[u] = 16.f * (float)(T.dim + 2) * 5.9604645e-8f * (sqrtf(n2) * 1.0001f + T.xnorm_max);
             uint32_t kb = (uint32_t)(P.state[(size_t)(q_begin + qi) * P.K + P.K - 1] >> 32);
-            thr2[u] = __uint_as_float(kb) * 1.00001f;  // K-th d2 after the seed (FLT_MAX -> inf: never prunes)
+            float kth2 = __uint_as_float(kb);
+            if (P.ext_bound) kth2 = fminf(kth2, P.ext_bound[qid]);
+            thr2[u] = kth2 * 1.00001f;  // K-th d2 after the seed (FLT_MAX -> inf: never prunes)
         } else {
             for (int j = 0; j < dpad; j++) qs[j * TQ + qi] = 0.f;
         }
@@ -1048,11 +1012,11 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams P) {
 // merge of per-shard partial lists (sharded-dataset mode): n_lists sorted key lists per query -> final arrays
 // thread per query; lists laid out [n_lists][nq][K].
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_merge_partial(DevTree T, const uint64_t* __restrict__ keys, int n_lists, int nq, int K, int* __restrict__ idx_out,
+__global__ void k_merge_partial(DevTree T, const uint64_t* __restrict__ keys, int n_lists, int nq, int K, int brute_keys, int* __restrict__ idx_out,
                                 float* __restrict__ d2_out, float* __restrict__ dist_out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
-    int head[16];
+    int head[kMaxShards];
     for (int l = 0; l < n_lists; l++) head[l] = 0;
     for (int k = 0; k < K; k++) {
         uint64_t best = ~0ull;
@@ -1069,7 +1033,7 @@ __global__ void k_merge_partial(DevTree T, const uint64_t* __restrict__ keys, in
             for (int l = 0; l < n_lists; l++)
                 if (head[l] < K && keys[((size_t)l * nq + i) * K + head[l]] == best) head[l]++;
             if (best != kEmptyKey) {
-                idx = T.orig_idx[(uint32_t)best & 0x7fffffffu];
+                idx = brute_keys ? (int)(uint32_t)best : T.orig_idx[(uint32_t)best & 0x7fffffffu];  // brute-force keys carry the original index
                 d2 = __uint_as_float((uint32_t)(best >> 32));
             }
         }
@@ -1077,6 +1041,37 @@ __global__ void k_merge_partial(DevTree T, const uint64_t* __restrict__ keys, in
         d2_out[(size_t)i * K + k] = d2;
         if (dist_out) dist_out[(size_t)i * K + k] = __fsqrt_rn(d2);
     }
+}
+
+// bound[qid] = K-th squared distance of the query's list after the seed scan (FLT_MAX while the list is not full)
+__global__ void k_extract_bounds(const uint64_t* __restrict__ state, const int* __restrict__ q_order, int nq, int K, float* __restrict__ bound) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nq) return;
+    bound[q_order[slot]] = __uint_as_float((uint32_t)(state[(size_t)slot * K + K - 1] >> 32));
+}
+// out[i] = min over the n arrays (sharded-dataset mode: the seed bounds of all shards; peer pointers are read over NVLink)
+struct BoundPtrs {
+    const float* p[kMaxShards];
+};
+__global__ void k_min_bounds(BoundPtrs B, int n, int nq, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float m = 3.402823466e+38f;
+    for (int l = 0; l < n; l++) m = fminf(m, B.p[l][i]);
+    out[i] = m;
+}
+// keeps only the keys whose position lies in [pos_lo, pos_hi) (order preserved), or empties the lists (pos_hi <= pos_lo)
+__global__ void k_clip_state(uint64_t* __restrict__ state, int nq, int K, int pos_lo, int pos_hi) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nq) return;
+    uint64_t* L = state + (size_t)slot * K;
+    int w = 0;
+    for (int k = 0; k < K; k++) {
+        const uint64_t key = L[k];
+        const int pos = (int)((uint32_t)key & 0x7fffffffu);
+        if (key != kEmptyKey && pos >= pos_lo && pos < pos_hi) L[w++] = key;
+    }
+    for (; w < K; w++) L[w] = kEmptyKey;
 }
 
 }  // namespace scht

@@ -1,0 +1,217 @@
+// Page selection for the tensor-core prefilter scan: which SCAN pages can hold a neighbour of some query of a tile?
+//
+// The scan-order image (ScanImage, scht_types.cuh) keeps the resident points in spatially tight groups; every group and
+// every scan page (256 slots) has a bounding ball (centre c, radius r).  For a query q with current K-th distance kth
+// (after the seed scan of its approximate leaf, Code/CPU_Convex_Tree.h:181-217) the triangle inequality gives the lower
+// bound  |q - p| >= |q - c| - r  for every point p of the ball, so the page is skipped when |q - c| - r > kth -- the
+// same role as the reference's hyper-plane test (Code/ConvexNode.h:113-144: skip a leaf whose lower bound exceeds the
+// K-th distance), with a bound that stays tight on clustered data where a leaf's half-spaces are loose.  All
+// comparisons carry the rounding slack ball_eps(dim), so a page holding a true neighbour is never skipped; which pages
+// are scanned never changes a result bit (DESIGN.md "Result contract").
+//
+// One CTA per 128-query tile (thread = query).  Level 1: every group ball against every query; level 2: the pages of
+// the groups that survive for at least one query, tested by the queries that need the group.  Output: ascending page
+// ranges per tile in the layout PageWalk reads ([kMaxCuts][kJobRanges] flat = kRangeCap ranges); overflow widens the
+// last range (scans more, stays exact).
+#pragma once
+#include "scht_kernels.cuh"
+
+namespace scht {
+
+struct SelectParams {
+    DevTree T;
+    ScanImage I;
+    const float* q;
+    const int* q_order;
+    int nq, K;
+    const uint64_t* state;    // [nq][K] keys by bucket slot (after the seed scan)
+    const float* ext_bound;   // [nq] by query id: external upper bound of the K-th distance^2 (or null)
+    int2* ranges;             // [n_tiles][kRangeCap]
+    int* n_ranges;            // [n_tiles][kMaxCuts]
+    int sel_mode, sel_step;   // tile subset (tile_of_selection)
+    unsigned long long* counters;  // [4] ball tests (per query), [5] pages listed x queries
+};
+
+constexpr int kSelQ = 128;    // queries per tile (= kTcQ)
+constexpr int kSelGroups = 16;  // group balls staged per round
+constexpr int kSelPages = 8;    // page balls staged per round
+
+__host__ __device__ inline size_t select_smem_bytes(int dp_regs, int dpad) {
+    const int ds = dp_regs > 0 ? dp_regs : dpad;
+    size_t b = (size_t)kSelGroups * ds * 4 + kSelGroups * 4;
+    if (dp_regs == 0) b += (size_t)dpad * kSelQ * 4;
+    return b + 16;
+}
+
+// DP > 0: dpad <= DP and the query lives in registers as DP/2 packed pairs; DP == 0: any dpad, query in shared memory
+template <int DP>
+__global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    __shared__ unsigned int s_mask;
+    __shared__ int s_nout;
+    const DevTree& T = P.T;
+    const ScanImage& I = P.I;
+    const int dpad = T.dpad;
+    const int DS = DP > 0 ? DP : dpad;                    // staged row length (floats), a multiple of 4
+    float* cs = reinterpret_cast<float*>(sel_smem);       // [kSelGroups][DS] staged centres
+    float* rs = cs + (size_t)kSelGroups * DS;             // [kSelGroups] staged radii
+    float* qs = rs + kSelGroups;                          // DP == 0: [dpad][kSelQ]
+    const int t = threadIdx.x, lane = t & 31;
+    const int n_tiles = (P.nq + kSelQ - 1) / kSelQ;
+    const int tile = tile_of_selection((int)blockIdx.x, P.sel_mode, P.sel_step);
+    if (tile >= n_tiles) return;
+    const int q_begin = tile * kSelQ;
+    const int nq_tile = min(kSelQ, P.nq - q_begin);
+    const bool valid = t < nq_tile;
+    const float e = ball_eps(T.dim);
+
+    // ---- the query and its bound ----
+    const int qid = valid ? P.q_order[q_begin + t] : -1;
+    uint64_t qreg[DP > 0 ? DP / 2 : 1];
+    if (DP > 0) {
+#pragma unroll
+        for (int j2 = 0; j2 < (DP > 0 ? DP / 2 : 1); j2++) {
+            const float a = (valid && 2 * j2 < T.dim) ? P.q[(size_t)qid * T.dim + 2 * j2] : 0.f;
+            const float b = (valid && 2 * j2 + 1 < T.dim) ? P.q[(size_t)qid * T.dim + 2 * j2 + 1] : 0.f;
+            qreg[j2] = pack2(a, b);
+        }
+    } else {
+        for (int j = 0; j < dpad; j++) qs[j * kSelQ + t] = (valid && j < T.dim) ? P.q[(size_t)qid * T.dim + j] : 0.f;
+    }
+    float thr = -1.f;  // padded slot: needs nothing
+    if (valid) {
+        float kth2 = __uint_as_float((uint32_t)(P.state[(size_t)(q_begin + t) * P.K + P.K - 1] >> 32));
+        if (P.ext_bound) kth2 = fminf(kth2, P.ext_bound[qid]);
+        thr = sqrtf(kth2) * (1.f + e) * (1.f + e);  // FLT_MAX (list not full) -> 1.8e19: nothing is skipped
+    }
+    if (t == 0) s_mask = 0u;
+    __syncthreads();
+
+    // squared distance of this thread's query to a staged centre row
+    auto dist2 = [&](const float* c) -> float {
+        if (DP > 0) {
+            uint64_t a0 = pack2(0.f, 0.f), a1 = a0;
+#pragma unroll
+            for (int j4 = 0; j4 < (DP > 0 ? DP / 4 : 1); j4++) {
+                const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(c + 4 * j4);
+                const uint64_t d0 = sub2(qreg[2 * j4], c2.x), d1 = sub2(qreg[2 * j4 + 1], c2.y);
+                a0 = fma2(d0, d0, a0);
+                a1 = fma2(d1, d1, a1);
+            }
+            float x0, x1, y0, y1;
+            unpack2(a0, x0, x1);
+            unpack2(a1, y0, y1);
+            return (x0 + x1) + (y0 + y1);
+        } else {
+            float a0 = 0.f, a1 = 0.f;
+            for (int j = 0; j < dpad; j += 2) {
+                const float d0 = qs[j * kSelQ + t] - c[j], d1 = qs[(j + 1) * kSelQ + t] - c[j + 1];
+                a0 = fmaf(d0, d0, a0);
+                a1 = fmaf(d1, d1, a1);
+            }
+            return a0 + a1;
+        }
+    };
+    // true when the ball (centre row c, radius r) may hold a point within this query's bound
+    auto needs = [&](const float* c, float r) -> bool {
+        const float dc = sqrtf(dist2(c));
+        return !((dc * (1.f - e) - r * (1.f + e)) > thr);  // NaN / inf never skip
+    };
+    // stage n balls (rows of `cen`, radii `rad`) starting at index i0
+    auto stage = [&](const float* cen, const float* rad, int i0, int n) {
+        for (int x = t; x < n * DS; x += kSelQ) {
+            const int r = x / DS, j = x - r * DS;
+            cs[x] = (j < dpad) ? cen[(size_t)(i0 + r) * dpad + j] : 0.f;
+        }
+        if (t < n) rs[t] = rad[i0 + t];
+    };
+
+    int2* out = P.ranges + (size_t)tile * kRangeCap;
+    int n_out = 0, cur_b = -1, cur_e = -1;  // thread 0 only
+    unsigned long long listed = 0, tests = 0;
+    auto flush = [&]() {
+        if (n_out == kRangeCap) {
+            listed += (unsigned long long)(cur_e - out[n_out - 1].y);
+            out[n_out - 1].y = cur_e;
+        } else {
+            listed += (unsigned long long)(cur_e - cur_b);
+            out[n_out++] = make_int2(cur_b, cur_e);
+        }
+    };
+    auto add_page = [&](int pg) {  // pages arrive in ascending order (a boundary page may repeat)
+        if (cur_b < 0) {
+            cur_b = pg;
+            cur_e = pg + 1;
+        } else if (pg <= cur_e) {
+            cur_e = max(cur_e, pg + 1);
+        } else {
+            flush();
+            cur_b = pg;
+            cur_e = pg + 1;
+        }
+    };
+
+    for (int g0 = 0; g0 < I.n_groups; g0 += kSelGroups) {
+        const int ng = min(kSelGroups, I.n_groups - g0);
+        __syncthreads();  // previous round's readers of cs are done
+        stage(I.gcen, I.grad, g0, ng);
+        __syncthreads();
+        unsigned int gm = 0;
+        if (valid)
+            for (int gi = 0; gi < ng; gi++)
+                if (needs(cs + (size_t)gi * DS, rs[gi])) gm |= 1u << gi;
+        tests += (unsigned long long)ng;
+        const unsigned int wm = __reduce_or_sync(0xffffffffu, gm);
+        if (lane == 0 && wm) atomicOr(&s_mask, wm);
+        __syncthreads();
+        unsigned int tile_mask = s_mask;
+        __syncthreads();
+        if (t == 0) s_mask = 0u;
+        while (tile_mask) {  // block-uniform: the groups some query of the tile needs
+            const int gi = __ffs(tile_mask) - 1;
+            tile_mask &= tile_mask - 1;
+            const int g = g0 + gi;
+            const int sb = I.gslot[g], se = I.gslot[g + 1];
+            if (se <= sb) continue;
+            const bool mine = (gm >> gi) & 1u;
+            const int pb = sb >> 8, pe = (se + kPage - 1) >> 8;
+            for (int p0 = pb; p0 < pe; p0 += kSelPages) {
+                const int np = min(kSelPages, pe - p0);
+                __syncthreads();  // cs free; s_mask reset visible
+                stage(I.pcen, I.prad, p0, np);
+                __syncthreads();
+                unsigned int pm = 0;
+                if (mine)
+                    for (int pi = 0; pi < np; pi++)
+                        if (needs(cs + (size_t)pi * DS, rs[pi])) pm |= 1u << pi;
+                if (mine) tests += (unsigned long long)np;
+                const unsigned int wpm = __reduce_or_sync(0xffffffffu, pm);
+                if (lane == 0 && wpm) atomicOr(&s_mask, wpm);
+                __syncthreads();
+                if (t == 0) {
+                    unsigned int m = s_mask;
+                    s_mask = 0u;
+                    while (m) {
+                        const int pi = __ffs(m) - 1;
+                        m &= m - 1;
+                        add_page(p0 + pi);
+                    }
+                }
+            }
+        }
+    }
+    if (t == 0) {
+        if (cur_b >= 0) flush();
+        s_nout = n_out;
+    }
+    __syncthreads();
+    const int total = s_nout;
+    if (t < kMaxCuts) P.n_ranges[(size_t)tile * kMaxCuts + t] = max(0, min(kJobRanges, total - t * kJobRanges));
+    if (P.counters) {
+        for (int o = 16; o; o >>= 1) tests += __shfl_xor_sync(0xffffffffu, tests, o);
+        if (lane == 0) atomicAdd(&P.counters[4], tests);
+        if (t == 0) atomicAdd(&P.counters[5], listed * (unsigned long long)nq_tile);
+    }
+}
+
+}  // namespace scht

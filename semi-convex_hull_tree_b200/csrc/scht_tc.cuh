@@ -48,14 +48,8 @@ constexpr int kTcQueueCap = 256;   // ring entries per epilogue warp (power of t
 
 struct TcScanParams {
     ScanParams S;            // q, q_order, q_leaf, nq, K, write_mode, pos range, ranges (tile = 128 queries), state, outputs
-    const unsigned char* tcpages;  // per page: FP16 image [kp/8][32][8][8] (kp*512 B): s p'_j, then norm hi/mid/lo
-    const float* mean;       // [dpad]
-    const float* pmax;       // [dpad] max |p_j - mean_j|
-    float pnorm_max;         // max |p - mean|_2
-    float pabs_sum;          // sum_j pmax_j
-    float scale;             // s (power of two)
-    float norm_unit;         // power of two u: the norm slots hold s^2|p'|^2 / u, the query operand holds u
-    int kp;                  // padded K (multiple of 16) = ceil16(dim + 3)
+    ScanImage I;             // the scan-order image: FP16 pages, slot -> position, centre / scale of the operands
+    int brute;               // 1: keys carry the ORIGINAL index and no approximate-leaf bit (scht_brute_force)
     int n_stages;            // slice stages in shared memory (3..kTcMaxStages)
     int n_seg;               // page segments per tile (>= 1): CTA b scans segment b / n_tiles of tile b % n_tiles and, when
     int seg_pages;           //   n_seg > 1, writes its key lists to S.keys_out[segment][query][K] (merged by k_merge_partial);
@@ -63,8 +57,6 @@ struct TcScanParams {
     int debug;               // SCHT_TC_PROF builds only: 1 = no pair passes the filter, 2 = also skip the min tree
     long long* trace;        // SCHT_TC_PROF builds: [64 pages][8] clock64 stamps of tile 0 (pages 2000..2063)
 };
-
-__host__ __device__ inline size_t tc_page_bytes(int kp) { return (size_t)kp * 512; }
 
 __host__ __device__ inline size_t tc_smem_bytes(int dpad, int kp, int K, int n_stages) {
     size_t b = 1024;                                                         // alignment slack
@@ -117,42 +109,16 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // -------------------------------------------------------------------------------------------------------------
-// builder of the tensor-core page image from the exact dim-major pages (one thread per sorted position)
-// -------------------------------------------------------------------------------------------------------------
-__global__ void k_build_tcpages(DevTree T, const float* __restrict__ mean, float scale, float norm_unit, int kp,
-                                unsigned char* __restrict__ tcpages) {
-    int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= (int64_t)T.n_pages * kPage) return;
-    int page = (int)(pos / kPage), r = (int)(pos % kPage);
-    const float* src = T.pages + (size_t)page * T.dpad * kPage + r;
-    __half* img = reinterpret_cast<__half*>(tcpages + (size_t)page * tc_page_bytes(kp));
-    const bool real = pos < T.n_points;
-    double n2 = 0.0, rest = 0.0;
-    for (int k = 0; k < kp; k++) {
-        __half hv = __float2half_rn(0.f);
-        if (k < T.dim) {
-            if (real) {
-                double c = (double)src[(size_t)k * kPage] - (double)mean[k];
-                n2 += c * c;
-                hv = __float2half_rn((float)(c * (double)scale));
-            }
-        } else if (k < T.dim + 3) {
-            // s^2 |p'|^2 / u as hi + mid + lo (each FP16, together 33 bits); padded positions: a value no bound reaches
-            if (k == T.dim) rest = real ? n2 * (double)scale * (double)scale / (double)norm_unit : 60000.0;
-            hv = __float2half_rn((float)rest);
-            rest -= (double)__half2float(hv);
-        }
-        img[(((size_t)(k >> 3) * 32 + (r >> 3)) * 8 + (r & 7)) * 8 + (k & 7)] = hv;
-    }
-}
-
-// -------------------------------------------------------------------------------------------------------------
 // per-query rounding margin of the filter (unscaled units):
-//   |S/s^2 + |q'|^2 - |p-q|^2| <= 2(2^-10+2^-21) B + 2^-19 (2B + Nmax) + subnormal term,   B >= sum_j |q'_j p'_j|
+//   |S/s^2 + |q'|^2 - |p-q|^2| <= 2(2^-10+2^-21) B + a(kp) (2B + Nmax) + subnormal term,   B >= sum_j |q'_j p'_j|
+// a(kp) covers the FP32 accumulation inside the tensor core (truncating adds, one per K16 step and a short tree inside a
+// step): measured <= 1.6 2^-23 sum|a_i b_i| for kp <= 144 (tools/tc_probe.cu), bounded here by max(16, 4 kp/16) 2^-23, i.e.
+// it grows with the number of K16 steps instead of trusting the measurement beyond the probed range.
 // -------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float tc_margin(float abs_sum_pmax, float qnorm, float q_l1, float pnorm_max, float pabs_sum, float scale) {
+__device__ __forceinline__ float tc_margin(float abs_sum_pmax, float qnorm, float q_l1, float pnorm_max, float pabs_sum, float scale, int kp) {
     float B = fminf(abs_sum_pmax, qnorm * pnorm_max);
-    float m = 2.0f * (9.765625e-4f + 4.7683716e-7f) * B + 1.9073486e-6f * (2.0f * B + pnorm_max * pnorm_max);
+    const float acc_term = fmaxf(16.f, 4.f * (float)(kp >> 4)) * 1.1920929e-7f;
+    float m = 2.0f * (9.765625e-4f + 4.7683716e-7f) * B + acc_term * (2.0f * B + pnorm_max * pnorm_max);
     m += 1.1920929e-7f * (q_l1 + pabs_sum) / scale;  // FP16 subnormals: absolute error 2^-25 per scaled operand
     return m * 1.01f;
 }
@@ -160,9 +126,11 @@ __device__ __forceinline__ float tc_margin(float abs_sum_pmax, float qnorm, floa
 // eligibility: the prefilter pays off when its error margin is small against the K-th distance after the seed scan.
 // counters[6] += queries whose margin is below 1/4 of the seed K-th distance^2 (and which fit FP16's range): even then
 // the survivors are a tiny fraction of the pairs, and a prefilter page costs ~1/10 of an exact page
-__global__ void k_tc_eligibility(DevTree T, const float* __restrict__ q, const int* __restrict__ q_order, int nq, int K,
-                                 const uint64_t* __restrict__ state, const float* __restrict__ mean, const float* __restrict__ pmax,
-                                 float pnorm_max, float pabs_sum, float scale, unsigned long long* __restrict__ counters) {
+__global__ void k_tc_eligibility(DevTree T, ScanImage I, const float* __restrict__ q, const int* __restrict__ q_order, int nq, int K,
+                                 const uint64_t* __restrict__ state, const float* __restrict__ ext_bound, unsigned long long* __restrict__ counters) {
+    const float* __restrict__ mean = I.mean;
+    const float* __restrict__ pmax = I.pmax;
+    const float pnorm_max = I.pnorm_max, pabs_sum = I.pabs_sum, scale = I.scale;
     int slot = blockIdx.x * blockDim.x + threadIdx.x;
     bool ok = false;
     if (slot < nq) {
@@ -175,8 +143,9 @@ __global__ void k_tc_eligibility(DevTree T, const float* __restrict__ q, const i
             l1 += fabsf(c);
             amax = fmaxf(amax, fabsf(c));
         }
-        float margin = tc_margin(s1 * 1.0001f, sqrtf(n2) * 1.0001f, l1 * 1.0001f, pnorm_max, pabs_sum, scale);
+        float margin = tc_margin(s1 * 1.0001f, sqrtf(n2) * 1.0001f, l1 * 1.0001f, pnorm_max, pabs_sum, scale, I.kp);
         float kth = __uint_as_float((uint32_t)(state[(size_t)slot * K + K - 1] >> 32));
+        if (ext_bound) kth = fminf(kth, ext_bound[qid]);
         ok = (kth < 3.0e38f) && (margin * 4.f <= kth) && (2.f * amax * scale < 60000.f);
     }
     unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -208,7 +177,8 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
     static_assert(!N256 || N_ISS == 2, "whole-page chains: one issuer per page parity");
     const ScanParams& P = TP.S;
     const DevTree& T = P.T;
-    const int dpad = T.dpad, K = P.K, kp = TP.kp;
+    const ScanImage& I = TP.I;
+    const int dpad = T.dpad, K = P.K, kp = I.kp;
     // (no manual re-alignment: the no-swizzle UMMA layout and cp.async.bulk need 16 bytes only, and a pointer that is
     // visibly derived from the __shared__ array keeps every access below an LDS/STS/ATOMS instead of a generic LD/ST/ATOM)
     extern __shared__ __align__(128) unsigned char smem_dyn[];
@@ -244,7 +214,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
     // that are neighbours in bucket order (same approximate leaf, same cluster, hot on the same pages) are dealt round-robin to the
     // four lane quadrants, so a burst of survivors is shared by all four rescorers instead of filling one quadrant's rings
     auto ord = [](int slot) { return ((slot & 31) << 2) | (slot >> 5); };
-    const float scale = TP.scale;
+    const float scale = I.scale;
 
     // ---- set-up ---------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -284,10 +254,10 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
         if (qids[qi] >= 0 && k < T.dim) {
             const float* qrow = P.q + (size_t)qids[qi] * T.dim;
             bool in_range = true;
-            for (int j = 0; j < T.dim; j++) in_range &= fabsf(qrow[j] - TP.mean[j]) * 2.f * scale < 60000.f;
-            if (in_range) v = (float)(-2.0 * ((double)qrow[k] - (double)TP.mean[k]) * (double)scale);
+            for (int j = 0; j < T.dim; j++) in_range &= fabsf(qrow[j] - I.mean[j]) * 2.f * scale < 60000.f;
+            if (in_range) v = (float)(-2.0 * ((double)qrow[k] - (double)I.mean[k]) * (double)scale);
         } else if (k >= T.dim && k < T.dim + 3) {
-            v = TP.norm_unit;  // multiplies the norm slots of the point operand (every row, also padded ones)
+            v = I.norm_unit;  // multiplies the norm slots of the point operand (every row, also padded ones)
         }
         sA[(((size_t)(k >> 3) * (kTcQ / 8) + (qi >> 3)) * 8 + (qi & 7)) * 8 + (k & 7)] = __float2half_rn(v);
     }
@@ -306,7 +276,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
     // these 128 queries only.  Re-scanning is cheap in this kernel and list insertion is idempotent.
     const int w_lo = (TP.n_seg > 1) ? TP.seg_page0 + seg * TP.seg_pages : 0;
     const int w_hi = (TP.n_seg > 1) ? ((seg == TP.n_seg - 1) ? 0x7fffffff : w_lo + TP.seg_pages) : 0x7fffffff;
-    PageWalk walk(P.ranges + (size_t)tile * kRangeCap, P.n_ranges + (size_t)tile * kMaxCuts, T.n_cuts, kJobRanges, nullptr, 0, w_lo, w_hi);
+    PageWalk walk(P.ranges + (size_t)tile * kRangeCap, P.n_ranges + (size_t)tile * kMaxCuts, P.range_groups, kJobRanges, nullptr, 0, w_lo, w_hi);
     const int n_slices = (kp + kTcKSlice - 1) / kTcKSlice;
     int page, run_lo, run_hi;
 
@@ -316,7 +286,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             uint32_t st = 0, ph = 0, ppg = 0;  // stage ring position, kept incrementally (a division per page would sit on this warp's critical path)
             const size_t page_bytes = tc_page_bytes(kp);
             while (walk.next_range(run_lo, run_hi)) for (page = run_lo; page < run_hi; page++) {
-                const unsigned char* src = TP.tcpages + (size_t)page * page_bytes;
+                const unsigned char* src = I.tcpages + (size_t)page * page_bytes;
                 for (int s = 0; s < n_slices; s++) {
                     mbar_wait(&empty_b[st], ph ^ 1);
                     TC_STAMP(s == 0, ppg, 0);
@@ -427,16 +397,19 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
         float qn2 = 0.f, s1 = 0.f, l1 = 0.f, amax = 0.f;
         const float* my_qrow = P.q + (size_t)(valid_q ? qids[qi] : 0) * T.dim;
         for (int j = 0; j < T.dim; j++) {
-            float c = valid_q ? (float)((double)my_qrow[j] - (double)TP.mean[j]) : 0.f;
+            float c = valid_q ? (float)((double)my_qrow[j] - (double)I.mean[j]) : 0.f;
             qn2 = fmaf(c, c, qn2);
-            s1 = fmaf(fabsf(c), TP.pmax[j], s1);
+            s1 = fmaf(fabsf(c), I.pmax[j], s1);
             l1 += fabsf(c);
             amax = fmaxf(amax, fabsf(c));
         }
         const bool in_range = 2.f * amax * scale < 60000.f;
-        const float margin = tc_margin(s1 * 1.0001f, sqrtf(qn2) * 1.0001f, l1 * 1.0001f, TP.pnorm_max, TP.pabs_sum, scale) + qn2 * 1.0e-5f;
+        const float margin = tc_margin(s1 * 1.0001f, sqrtf(qn2) * 1.0001f, l1 * 1.0001f, I.pnorm_max, I.pabs_sum, scale, kp) + qn2 * 1.0e-5f;
         const float s2 = scale * scale;
+        // external upper bound of the K-th distance^2 (seed scan of another shard / of the tree for the brute-force entry)
+        const float ext_kth = (P.ext_bound && valid_q) ? P.ext_bound[qids[qi]] : 3.402823466e+38f;
         auto bound_of = [&](float kth) {
+            kth = fminf(kth, ext_kth);
             // S passes when S <= s^2 (kth(1+2^-20) - |q'|^2 + margin); padded query slots never pass; a query outside
             // FP16's range has a zero operand row and lets everything pass.  The bound is NOT clamped below the norm slots
             // of padded positions (60000 u): a real pair of a far query can lie above any such clamp, and a padded position
@@ -506,10 +479,13 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                     int pos = 0, cq = 0;
                     if (lane < n) {
                         const uint64_t e = ring[(head + off) & (kTcQueueCap - 1)];
-                        pos = (int)(uint32_t)e;
+                        pos = I.slot_pos[(uint32_t)e];  // ring entries name a SLOT of the scan-order image; -1: padding of the last page
                         cq = (int)(e >> 32);
                         const float* qq = P.q + (size_t)qids[quad * 32 + cq] * T.dim;  // the query's original coordinates
-                        if constexpr (ROWS) {
+                        if (pos < 0) {
+                            d2 = 3.402823466e+38f;  // rejected below
+                            pos = 0;
+                        } else if constexpr (ROWS) {
                             // wide points: the row-major copy (dpad*4 contiguous bytes; the dim-major pages cost one 32-byte
                             // sector per coordinate).  Loads first (16 dims at a time), then the sequential reference chain
                             const float4* pr = reinterpret_cast<const float4*>(T.rows + (size_t)pos * dpad);
@@ -563,7 +539,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                         int cpos = __shfl_sync(0xffffffffu, pos, src);
                         int ccq = __shfl_sync(0xffffffffu, cq, src);
                         const int a0 = a0s[quad * 32 + ccq], a1 = a1s[quad * 32 + ccq];
-                        uint32_t low = ((cpos >= a0 && cpos < a1) ? 0u : 0x80000000u) | (uint32_t)cpos;
+                        uint32_t low = TP.brute ? (uint32_t)T.orig_idx[cpos] : (((cpos >= a0 && cpos < a1) ? 0u : 0x80000000u) | (uint32_t)cpos);
                         uint64_t key = ((uint64_t)__float_as_uint(cd2) << 32) | low;
                         uint64_t* L = lists + (size_t)(quad * 32 + ccq) * K;
                         if (key < L[K - 1]) n_ins += list_insert(L, K, key, lane);
@@ -588,7 +564,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                         int idx = -1;
                         float d2 = 3.402823466e+38f;
                         if (key != kEmptyKey) {
-                            idx = T.orig_idx[(uint32_t)key & 0x7fffffffu];
+                            idx = TP.brute ? (int)(uint32_t)key : T.orig_idx[(uint32_t)key & 0x7fffffffu];
                             d2 = __uint_as_float((uint32_t)(key >> 32));
                         }
                         P.idx_out[(size_t)qid * K + k] = idx;
@@ -598,7 +574,8 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                 } else if (P.write_mode == kWriteState) {
                     for (int k = lane; k < K; k += 32) P.state[(size_t)(q_begin + ord(ql)) * K + k] = L[k];
                 } else {
-                    for (int k = lane; k < K; k += 32) P.keys_out[(size_t)qid * K + k] = L[k];
+                    uint64_t* dst = keys_dst(P, qid);  // plain key array, or the owner device's gather buffer (peer memory)
+                    for (int k = lane; k < K; k += 32) dst[k] = L[k];
                 }
             }
             if (P.counters) {
@@ -701,7 +678,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                 TC_STAMP(warp == 0, pg, 6);
                 process(va, col0 + 32);
                 TC_STAMP(warp == 0, pg, 7);
-                if (half == 0 && sub == 0) n_pairs += (unsigned long long)min(kPage, T.n_points - page * kPage);
+                if (half == 0 && sub == 0) n_pairs += (unsigned long long)min(kPage, I.n_slots - page * kPage);
                 pg++;
             }
             __syncwarp();

@@ -23,7 +23,7 @@ def test_every_declared_symbol_is_exported(pkg):
     for n in names:
         assert hasattr(lib, n), "libscht_b200.so does not export " + n
     assert sorted(pkg.SYMBOLS) == names, "python binding table out of sync with include/scht.h"
-    assert pkg.lib().scht_abi_version() == 1
+    assert pkg.lib().scht_abi_version() == 2
 
 
 def test_product_does_not_link_the_oracle(pkg):

@@ -1,0 +1,107 @@
+"""Full-size GPU parity (-m gpu) of every BASELINE.json configuration: the device answers the whole workload, a sample of
+>= 200 queries is compared bit for bit with the CPU oracle (oracle/scht_oracle.c, pinned to the reference by
+tests/test_oracle_golden.py), and the rest through size-independent properties -- tree query == exhaustive device scan
+(tie-free data), sorted lists, self-hits at distance 0.  Data sets are the ones bench.py times (same generators, same
+seeds), trees are built on the device (bit-identical to the host builder and the reference, tests/test_gpu_build.py)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def bench_module():
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    return importlib.import_module("bench")
+
+
+def sample_check(orc, ht, q, K, idx, d2, sample, what):
+    oi, od2, _, _, cnt = orc.knn(ht, q[sample], K, alg=2)
+    assert_bit_equal(idx[sample], oi, what + ": idx vs oracle sample")
+    assert_bit_equal(d2[sample], od2, what + ": dist2 vs oracle sample")
+    return cnt
+
+
+def test_cfg1_posture_like_full_oracle(pkg, orc):
+    """configs[0] stand-in (78 095 x 15 self-query, K=10, pct 0.005): EVERY query against the oracle"""
+    b = bench_module()
+    n, dim, nq, K, pct, kind = b.WORKLOADS["posture_like_78095x15_self_K10"]
+    data, q = b.make_data(kind, n, dim, nq, 1234)
+    ht = pkg.HostTree(data, pct, 1, device=0)
+    ix = pkg.Index(ht)
+    idx, d2, d = ix.query(q, K, want_dist=True)
+    oi, od2, od, _, _ = orc.knn(ht, q, K, alg=2)
+    assert_bit_equal(idx, oi, "idx")
+    assert_bit_equal(d2, od2, "dist2")
+    assert_bit_equal(d, od, "dist")
+    assert (d2[:, 0] == 0).all()  # self-query
+    ix.close()
+
+
+@pytest.mark.parametrize("K,nq", [(10, 1_000_000), (1, 250_000), (100, 250_000)])
+def test_cfg3_gauss_10Mx32(pkg, orc, K, nq):
+    """configs[2]: Gaussian clusters 10M x 32, K = 1 / 10 / 100"""
+    b = bench_module()
+    n, dim, _, _, pct, kind = b.WORKLOADS["gauss_10Mx32_q1M_K10"]
+    data, q = b.make_data(kind, n, dim, nq, 1234)
+    ht = pkg.HostTree(data, pct, 1, device=0)
+    ix = pkg.Index(ht)
+    idx, d2, st = ix.query(q, K, want_stats=True)
+    assert (np.diff(d2, axis=1) >= 0).all() and (idx >= 0).all() and (idx < n).all()
+    sample = np.arange(0, nq, nq // 240)[:240]
+    sample_check(orc, ht, q, K, idx, d2, sample, "cfg3 K=%d" % K)
+    # tree query == exhaustive device scan (continuous data: no ties) on another slice
+    sl = slice(nq // 2, nq // 2 + 20_000)
+    bi, bd2 = ix.brute_force(q[sl], K)
+    assert_bit_equal(idx[sl], bi, "tree vs exhaustive idx")
+    assert_bit_equal(d2[sl], bd2, "tree vs exhaustive dist2")
+    print("cfg3 K=%d: %.1f ms device for %d queries, scanned/query %.0f of %d, prefilter batches %d" % (
+        K, st["ms_device"], nq, st["dist_computations"] / nq, n, st["prefilter_batches"]))
+    ix.close()
+
+
+def test_cfg4_siftlike_1Mx128(pkg, orc):
+    """configs[3]: SIFT-like integers 1M x 128 (real ties): the tie order must be the reference's"""
+    b = bench_module()
+    n, dim, nq, K, pct, kind = b.WORKLOADS["siftlike_1Mx128_q100k_K10"]
+    data, q = b.make_data(kind, n, dim, nq, 1234)
+    ht = pkg.HostTree(data, pct, 1, device=0)
+    ix = pkg.Index(ht)
+    idx, d2, st = ix.query(q, K, want_stats=True)
+    assert (np.diff(d2, axis=1) >= 0).all()
+    sample = np.arange(0, nq, nq // 200)[:200]
+    sample_check(orc, ht, q, K, idx, d2, sample, "cfg4")
+    # distances (not indices: ties) equal the exhaustive scan's
+    bi, bd2 = ix.brute_force(q[:10_000], K)
+    assert_bit_equal(d2[:10_000], bd2, "tree vs exhaustive dist2")
+    ix.close()
+
+
+def test_cfg5_shaped_uniform_24Mx16(pkg, orc):
+    """configs[4] shape (uniform x 16, leaf <= 500) at 24M points: whole-data-set handle, and the same data set as a
+    sharded-dataset multi handle over the visible GPUs -- both bit-identical to the oracle sample and to each other"""
+    rng = np.random.default_rng(1234)
+    n, dim, nq, K = 24_000_000, 16, 100_000, 10
+    data = rng.random((n, dim), dtype=np.float32)
+    q = np.random.default_rng(2234).random((nq, dim), dtype=np.float32)
+    q[:500] = data[::48_000]
+    ht = pkg.HostTree(data, 500.5 / n, 1, device=0)
+    ix = pkg.Index(ht)
+    idx, d2 = ix.query(q, K)
+    assert (np.diff(d2, axis=1) >= 0).all()
+    assert (idx[:500, 0] == np.arange(0, n, 48_000)).all() and (d2[:500, 0] == 0).all()
+    sample = np.concatenate([np.arange(0, 100), np.arange(1000, nq, nq // 120)[:120]])
+    sample_check(orc, ht, q, K, idx, d2, sample, "cfg5-shaped")
+    ix.close()
+    devs = list(range(min(8, pkg.lib().scht_device_count())))
+    mx = pkg.Index(ht, devices=devs, mode=pkg.SHARD_DATASET)
+    midx, md2 = mx.query(q, K)
+    assert_bit_equal(midx, idx, "sharded-dataset idx")
+    assert_bit_equal(md2, d2, "sharded-dataset dist2")
+    mx.close()
