@@ -282,21 +282,29 @@ __device__ __forceinline__ int list_insert(uint64_t* L, int K, uint64_t key, int
     return 1;
 }
 
-// Ascending, merged page ranges covering the seed neighbourhoods of a tile's (leaf-sorted) queries.
+// Ascending, disjoint page ranges covering the seed neighbourhoods of a tile's queries.  The queries of a tile are
+// neighbours in BUCKET order (leaves ordered by scan group, DevTree::leaf_rank), so their neighbourhoods arrive in any
+// position order: insertion sort by first page, then merge what overlaps or touches (<= 64 entries, one thread).
 __device__ inline int build_seed_ranges(const int* a0s, const int* a1s, int nq_tile, int pos_lo, int pos_hi, int2* out) {
     int n = 0;
     for (int i = 0; i < nq_tile; i++) {
         int a0 = max(a0s[i], pos_lo), a1 = min(a1s[i], pos_hi);
         if (a1 <= a0) continue;
-        int pb = a0 / kPage, pe = (a1 + kPage - 1) / kPage;
-        if (n > 0 && pb <= out[n - 1].y) {
-            out[n - 1].y = max(out[n - 1].y, pe);
-            if (pb < out[n - 1].x) out[n - 1].x = pb;  // (neighbourhoods of leaf-sorted queries are nested or ascending)
-        } else {
-            out[n++] = make_int2(pb, pe);
+        const int2 r = make_int2(a0 / kPage, (a1 + kPage - 1) / kPage);
+        if (n > 0 && r.x == out[n - 1].x && r.y == out[n - 1].y) continue;  // same leaf as the previous query (the common case)
+        int j = n++;
+        while (j > 0 && out[j - 1].x > r.x) {
+            out[j] = out[j - 1];
+            j--;
         }
+        out[j] = r;
     }
-    return n;
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        if (m > 0 && out[i].x <= out[m - 1].y) out[m - 1].y = max(out[m - 1].y, out[i].y);
+        else out[m++] = out[i];
+    }
+    return m;
 }
 
 // Walks the pages of a tile in ascending order: the ranges of `n_groups` consecutive groups (group g holds cnt[g]

@@ -56,11 +56,15 @@ def test_cfg3_gauss_10Mx32(pkg, orc, K, nq):
     assert (np.diff(d2, axis=1) >= 0).all() and (idx >= 0).all() and (idx < n).all()
     sample = np.arange(0, nq, nq // 240)[:240]
     sample_check(orc, ht, q, K, idx, d2, sample, "cfg3 K=%d" % K)
-    # tree query == exhaustive device scan (continuous data: no ties) on another slice
+    # tree query == exhaustive device scan on another slice: distances always; indices where a list holds no equal
+    # distances (at this size a few float32 ties occur even on continuous data, and the two entries break them differently:
+    # approximate leaf / sorted position vs original index)
     sl = slice(nq // 2, nq // 2 + 20_000)
-    bi, bd2 = ix.brute_force(q[sl], K)
-    assert_bit_equal(idx[sl], bi, "tree vs exhaustive idx")
-    assert_bit_equal(d2[sl], bd2, "tree vs exhaustive dist2")
+    bi, bd2 = ix.brute_force(q[sl], K + 1)  # one more: a tie between the K-th and the (K+1)-th distance shows too
+    assert_bit_equal(d2[sl], bd2[:, :K], "tree vs exhaustive dist2")
+    no_tie = (np.diff(bd2, axis=1) > 0).all(axis=1)
+    assert no_tie.mean() > 0.99
+    assert_bit_equal(idx[sl][no_tie], bi[no_tie][:, :K], "tree vs exhaustive idx")
     print("cfg3 K=%d: %.1f ms device for %d queries, scanned/query %.0f of %d, prefilter batches %d" % (
         K, st["ms_device"], nq, st["dist_computations"] / nq, n, st["prefilter_batches"]))
     ix.close()

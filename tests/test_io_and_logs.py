@@ -44,6 +44,68 @@ def test_read_text_matches_reference_contract(pkg, tmp_path):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+REF_AUX = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_aux")
+needs_ref_aux = pytest.mark.skipif(not os.access(REF_AUX, os.X_OK), reason="oracle/_ref/ref_aux not built (reference sources absent)")
+
+
+def read_fmat(path):
+    raw = open(path, "rb").read()
+    rows, cols = struct.unpack("<ii", raw[:8])
+    return np.frombuffer(raw, dtype=np.float32, offset=8).reshape(rows, cols)
+
+
+@needs_ref_aux
+@pytest.mark.parametrize("delims", [" ", ",", "\t"])
+def test_read_text_vs_reference_read_data(pkg, tmp_path, delims):
+    """scht_read_text against the reference's own read_data (Code/data_processor.h:75-99, compiled unmodified into
+    oracle/_ref/ref_aux) on well-formed files: same shape, same float bits"""
+    import subprocess
+    rng = np.random.default_rng(7)
+    data = np.concatenate([(rng.standard_normal((700, 9)) * 10.0 ** rng.integers(-6, 7, (700, 1))).astype(np.float32),
+                           rng.integers(-300, 300, (300, 9)).astype(np.float32)])
+    lines = []
+    for r, row in enumerate(data):
+        toks = [("%.6f" % v) if (r + j) % 4 == 0 else ("%.8e" % v) if (r + j) % 4 == 1 else ("%d" % v) if float(v).is_integer() else repr(float(v))
+                for j, v in enumerate(row)]
+        lines.append(delims.join(toks))
+    p = tmp_path / "d.txt"
+    p.write_text("\n".join(lines) + "\n")
+    out = tmp_path / "ref.fmat"
+    subprocess.run([REF_AUX, "readdata", str(p), delims, str(out)], check=True, capture_output=True)
+    want = read_fmat(out)
+    got = pkg.read_text(str(p), delims)
+    assert got.shape == want.shape == (1000, 9)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # and a file written by scht_write_text is read back by the reference with the original bits
+    q = tmp_path / "w.txt"
+    pkg.write_text(str(q), data)
+    subprocess.run([REF_AUX, "readdata", str(q), " ", str(out)], check=True, capture_output=True)
+    assert np.array_equal(read_fmat(out).view(np.uint32), data.view(np.uint32))
+
+
+@needs_ref_aux
+@pytest.mark.parametrize("n,dim,pct,seed", [(2000, 4, 0.01, 1), (5000, 16, 0.004, 3), (777, 3, 0.1, 1)])
+def test_tree_info_vs_reference_save_tree_info(pkg, tmp_path, n, dim, pct, seed):
+    """scht_format_tree_info against the text the reference's own save_tree_info writes (Code/Convex_Tree.h:964-991) for the
+    same data and seed; only the build time differs"""
+    import subprocess
+    sys_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    import sys
+    if sys_path not in sys.path:
+        sys.path.insert(0, sys_path)
+    from io_formats import write_fmat
+    data = np.random.default_rng(n).random((n, dim), dtype=np.float32)
+    dp, out = tmp_path / "d.fmat", tmp_path / "info.txt"
+    write_fmat(str(dp), data)
+    subprocess.run([REF_AUX, "treeinfo", str(dp), repr(pct), str(seed), str(out)], check=True, capture_output=True)
+    want = out.read_text()
+    got = pkg.format_tree_info(pkg.HostTree(data, pct, seed=seed), pct)
+    marker = "tree building time:  "
+    assert marker in want and want.endswith("s\n")
+    assert got[:got.index(marker) + len(marker)] == want[:want.index(marker) + len(marker)]
+    assert got.endswith("s\n") and float(got[got.index(marker) + len(marker):-2]) >= 0.0
+
+
 def test_read_text_edge_cases(pkg, tmp_path):
     p = tmp_path / "e.txt"
     # no trailing newline, CRLF, a short line (zero-filled), a long line (extra tokens ignored), an empty line (a row)
