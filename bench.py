@@ -396,26 +396,17 @@ def multi_gpu_extras(pkg, dist, torch, ht, ix, queries0, dim, K, rank, local_ran
     stream = torch.cuda.current_stream().cuda_stream
     parts = sh.leaf_shards(ht.arrays()["leaf_count"], world)
     shard = pkg.Index(ht, device=local_rank, leaf_range=parts[rank])
+    ids = [pkg.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm = pkg.Comm(ids[0], rank, world, local_rank)  # the library's own NCCL communicator (scht_comm_create)
     dq = torch.from_numpy(queries0).to(dev)
-    bound = torch.empty(nq, dtype=torch.float32, device=dev)
-    keys = torch.empty((nq, K), dtype=torch.int64, device=dev)
-    qb, qe = sh.query_shard(nq, world, rank)
+    qb, qe = comm.query_slice(nq)
     idx = torch.empty((qe - qb, K), dtype=torch.int32, device=dev)
     d2 = torch.empty((qe - qb, K), dtype=torch.float32, device=dev)
-    a2a = sh.torch_all_to_all()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
-    def step(timed=False):
-        shard.partial_seed_device(dq.data_ptr(), nq, dim, K, bound.data_ptr(), stream)
-        dist.all_reduce(bound, op=dist.ReduceOp.MIN)
-        shard.partial_scan_device(dq.data_ptr(), nq, dim, K, bound.data_ptr(), keys.data_ptr(), stream)
-        if timed:
-            ev[2].record()
-        recv, _ = sh.exchange_partial_keys(keys, world, rank, a2a)
-        if timed:
-            ev[3].record()
-        stacked = torch.stack(recv).contiguous()  # [world][nq_mine][K]
-        shard.merge_partial_device(stacked.data_ptr(), world, qe - qb, dim, K, idx.data_ptr(), d2.data_ptr(), None, stream)
+    def step():  # seed scan -> ncclAllReduce(min) of the bounds -> shard scan -> grouped ncclSend/ncclRecv of the K-lists -> merge
+        comm.query_sharded_device(shard, dq.data_ptr(), nq, dim, K, idx.data_ptr(), d2.data_ptr(), None, stream)
 
     step()
     torch.cuda.synchronize()
@@ -426,7 +417,14 @@ def multi_gpu_extras(pkg, dist, torch, ht, ix, queries0, dim, K, rank, local_ran
         step()
     ev[1].record()
     torch.cuda.synchronize()
-    step(timed=True)
+    # the exchange alone (same payload through torch's all_to_all): what the NVLink fabric delivers for this message size
+    keys = torch.empty((nq, K), dtype=torch.int64, device=dev)
+    a2a = sh.torch_all_to_all()
+    sh.exchange_partial_keys(keys, world, rank, a2a)
+    torch.cuda.synchronize()
+    ev[2].record()
+    sh.exchange_partial_keys(keys, world, rank, a2a)
+    ev[3].record()
     torch.cuda.synchronize()
     t = torch.tensor([ev[0].elapsed_time(ev[1]) / steps, ev[2].elapsed_time(ev[3])], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -437,14 +435,17 @@ def multi_gpu_extras(pkg, dist, torch, ht, ix, queries0, dim, K, rank, local_ran
     ok = torch.tensor([int(torch.equal(ridx, idx) and torch.equal(rd2.view(torch.int32), d2.view(torch.int32)))], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     a2a_bytes = nq * K * 8 * (world - 1) // world
-    out["sharded_dataset"] = {"mode": "one process per GPU, leaf shards, NCCL all-reduce(min) of seed bounds + all-to-all of K-lists", "n_gpus": world,
+    out["sharded_dataset"] = {"mode": "one process per GPU, leaf shards; inside the library: ncclAllReduce(min) of the seed bounds, grouped "
+                                      "ncclSend/ncclRecv of the K-lists, merge per query slice (scht_query_sharded_device)", "n_gpus": world,
                               "queries": nq, "ms_per_step": float(t[0]), "queries_per_s": nq / (float(t[0]) / 1e3),
                               "all_to_all_bytes_per_rank": a2a_bytes, "all_to_all_ms": float(t[1]),
                               "all_to_all_GBps_per_rank": a2a_bytes / max(float(t[1]), 1e-6) / 1e6,
                               "shard_points": int(ht.arrays()["leaf_count"][parts[rank][0]:parts[rank][1]].sum()),
+                              "shard_device_MB": shard.info()["device_bytes"] >> 20,
                               "bit_identical_to_replicated_query": bool(ok.item())}
+    comm.close()
     shard.close()
-    del dq, keys, bound
+    del dq, keys
     torch.cuda.synchronize()
 
     # (2) single process, all GPUs: the other ranks wait on the host (a NCCL barrier would spin on their GPUs)

@@ -242,6 +242,24 @@ int scht_merge_partial_device(scht_handle* h, const uint64_t* d_keys, int32_t n_
                               int64_t n_queries, int32_t dim, int32_t K, int32_t* d_idx_out, float* d_dist2_out,
                               float* d_dist_out, void* cuda_stream);
 
+/* The same five steps inside the library, one process per GPU, NCCL over NVLink for steps 2 and 4 (libnccl.so.2 is loaded
+ * at run time, only by these entry points):
+ *   rank 0: scht_comm_unique_id(id) and hands the SCHT_COMM_ID_BYTES bytes to every rank (MPI, torch.distributed, a file ...)
+ *   every rank: scht_comm_create(id, rank, world, device, &comm); scht_create_shard(tree, device, its leaf range, &h)
+ *   per batch:  scht_query_sharded_device(h, comm, d_queries (ALL queries, same on every rank), ...) fills d_idx_out /
+ *               d_dist2_out / d_dist_out for the rank's contiguous query slice [begin, end) (scht_comm_query_slice;
+ *               the arrays hold (end - begin) * K elements).  Collective: every rank must call it with the same queries.
+ * Results are bit-identical to scht_query on a single GPU holding the whole tree. */
+#define SCHT_COMM_ID_BYTES 128
+typedef struct scht_comm scht_comm;
+int scht_comm_unique_id(void* id_out /* SCHT_COMM_ID_BYTES */);
+int scht_comm_create(const void* id, int32_t rank, int32_t world, int32_t device, scht_comm** out);
+void scht_comm_destroy(scht_comm* c);
+int scht_comm_query_slice(const scht_comm* c, int64_t n_queries, int64_t* begin, int64_t* end);
+int scht_query_sharded_device(scht_handle* h, scht_comm* c, const float* d_queries, int64_t n_queries, int32_t dim,
+                              int32_t K, int32_t* d_idx_out, float* d_dist2_out, float* d_dist_out, void* cuda_stream,
+                              scht_stats* stats);
+
 /* Tree facts of a handle (for logs: print_tree_info, Code/Convex_Tree.h:946-958). */
 int scht_handle_info(const scht_handle* h, int32_t* dim, int64_t* n_points, int32_t* n_nodes, int32_t* n_leaves,
                      int32_t* device, int64_t* device_bytes);

@@ -23,9 +23,16 @@
 template <typename T>
 class B200_Convex_Tree : public Convex_Tree<T> {
 public:
+    // device >= 0: that GPU; device == -1: every visible GPU, the queries of a kNN() call are sharded across them
     B200_Convex_Tree(Matrix<T>& data, FLOAT_TYPE leaf_pts_percent, int alg_type = USE_B200_LEAF_APPRXIMATE_QP, int device = 0)
         : Convex_Tree<T>(data, leaf_pts_percent, alg_type) {
-        flatten_and_upload(device);
+        flatten_and_upload(std::vector<int>(1, device), SCHT_SHARD_QUERIES);
+    }
+    // several GPUs behind the reference's interface: `devices` = CUDA ordinals (empty = all), mode = SCHT_SHARD_QUERIES (tree
+    // replicated, query slices) or SCHT_SHARD_DATASET (each GPU holds 1/n of the leaves; K-lists merged over NVLink)
+    B200_Convex_Tree(Matrix<T>& data, FLOAT_TYPE leaf_pts_percent, const std::vector<int>& devices, int mode, int alg_type = USE_B200_LEAF_APPRXIMATE_QP)
+        : Convex_Tree<T>(data, leaf_pts_percent, alg_type) {
+        flatten_and_upload(devices, mode);
     }
     virtual ~B200_Convex_Tree() { scht_destroy(dev_); }
 
@@ -67,7 +74,7 @@ private:
         if (rc != SCHT_OK) std::cout << "B200_Convex_Tree: " << scht_last_error() << std::endl;  // like check_cl_error: print, go on
     }
 
-    void flatten_and_upload(int device) {
+    void flatten_and_upload(const std::vector<int>& devices, int mode) {
         const int dim = this->m_data.ncols(), n = this->m_data.nrows(), nn = this->nodes_num, L = this->leaf_nodes_num;
         std::vector<int> leaf_start(L), leaf_count(L), leaf_node(L), left(nn), right(nn), parent(nn), leaf_index(nn), beta_off(nn + 1);
         std::vector<float> lc((size_t)nn * dim, 0.f), rc((size_t)nn * dim, 0.f), normal((size_t)nn * dim, 0.f), beta;
@@ -104,7 +111,9 @@ private:
         d.node_left = left.data(); d.node_right = right.data(); d.node_parent = parent.data(); d.node_leaf_index = leaf_index.data();
         d.node_left_center = lc.data(); d.node_right_center = rc.data(); d.node_normal = normal.data();
         d.node_beta_off = beta_off.data(); d.node_beta = beta.data();
-        if (scht_create(&d, device, &dev_) != SCHT_OK) {
+        const bool one = devices.size() == 1 && mode == SCHT_SHARD_QUERIES;
+        int status = one ? scht_create(&d, devices[0], &dev_) : scht_create_multi(&d, devices.empty() ? 0 : devices.data(), (int)devices.size(), mode, &dev_);
+        if (status != SCHT_OK) {
             std::cout << "B200_Convex_Tree: " << scht_last_error() << std::endl;
             dev_ = 0;
         }

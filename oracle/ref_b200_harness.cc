@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 extern "C" {
 cl_int clGetPlatformIDs(cl_uint, cl_platform_id*, cl_uint*) { return -1; }
@@ -59,19 +60,31 @@ static void put_rec(FILE* f, const char* name, int dtype, int64_t count, const v
 }
 
 int main(int argc, char** argv) {
-    if (argc != 8) {
-        fprintf(stderr, "ref_b200_knn <data.fmat> <pct> <seed> <queries.fmat> <K> <brute 0|1> <out.knn>\n");
+    if (argc < 8 || argc > 11) {
+        fprintf(stderr, "ref_b200_knn <data.fmat> <pct> <seed> <queries.fmat> <K> <brute 0|1> <out.knn> [n_gpus (0 = device 0 only) [mode 0|1 [reps]]]\n");
         return 1;
     }
+    const int n_gpus = argc > 8 ? atoi(argv[8]) : 0, mode = argc > 9 ? atoi(argv[9]) : 0, reps = argc > 10 ? atoi(argv[10]) : 1;
     std::cout.setstate(std::ios_base::failbit);
     Matrix<float> data = read_fmat(argv[1]);
     float pct = (float)atof(argv[2]);
     Matrix<float> q = read_fmat(argv[4]);
     int K = atoi(argv[5]), brute = atoi(argv[6]);
     srand((unsigned)atoi(argv[3]));
-    Convex_Tree<float>* t = new B200_Convex_Tree<float>(data, pct);   // used through the reference's base-class interface
+    // used through the reference's base-class interface; n_gpus > 0: that many GPUs behind the same class
+    std::vector<int> devs;
+    for (int i = 0; i < n_gpus; i++) devs.push_back(i);
+    Convex_Tree<float>* t = n_gpus > 0 ? new B200_Convex_Tree<float>(data, pct, devs, mode) : new B200_Convex_Tree<float>(data, pct);
     t->set_batch_size(1000000);
-    if (brute) t->brute_force_kNN(q, K); else t->kNN(q, K);
+    // reps > 1: the same call repeated (the results of a call are owned by the tree and replaced by the next one); the time of
+    // the LAST call goes to stderr -- end to end through the drop-in: pageable Matrix<T> in, std::vector results out
+    for (int r = 0; r < reps; r++) {
+        struct timespec a, b;
+        clock_gettime(CLOCK_MONOTONIC, &a);
+        if (brute) t->brute_force_kNN(q, K); else t->kNN(q, K);
+        clock_gettime(CLOCK_MONOTONIC, &b);
+        if (r == reps - 1) fprintf(stderr, "ref_b200_knn: call_ms=%.3f queries=%u K=%d n_gpus=%d mode=%d\n", (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6, q.nrows(), K, n_gpus, mode);
+    }
     int nq = (int)q.nrows();
     std::vector<int32_t> idx((size_t)nq * K);
     std::vector<float> d2((size_t)nq * K), d((size_t)nq * K);

@@ -81,6 +81,12 @@ SYMBOLS = {
     "scht_merge_partial_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scht_handle_info": (C.c_int, [C.c_void_p, i32p, C.POINTER(C.c_int64), i32p, i32p, i32p, C.POINTER(C.c_int64)]),
+    "scht_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "scht_comm_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "scht_comm_destroy": (None, [C.c_void_p]),
+    "scht_comm_query_slice": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "scht_query_sharded_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "scht_handle_layout": (C.c_int, [C.c_void_p, i32p, i32p, i32p, C.POINTER(C.c_int64), i32p, i32p]),
     "scht_read_text": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(f32p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "scht_write_text": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
@@ -333,6 +339,38 @@ class Index:
             self.close()
         except Exception:
             pass
+
+
+class Comm:
+    """scht_comm: NCCL communicator of the library for the sharded-dataset mode with one process per GPU.
+    `id_bytes` = Comm.unique_id() of rank 0, distributed by the caller (e.g. torch.distributed.broadcast)."""
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(Comm.ID_BYTES)
+        _check(lib().scht_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, id_bytes, rank, world, device):
+        self._c = C.c_void_p()
+        self.rank, self.world = rank, world
+        _check(lib().scht_comm_create(C.c_char_p(bytes(id_bytes)), rank, world, int(device), C.byref(self._c)))
+
+    def query_slice(self, nq):
+        b, e = C.c_int64(), C.c_int64()
+        _check(lib().scht_comm_query_slice(self._c, nq, C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def query_sharded_device(self, index, q_ptr, nq, dim, K, idx_ptr, d2_ptr, dist_ptr=None, stream=None, stats=None):
+        """scht_query_sharded_device: collective; fills the outputs for this rank's query slice"""
+        _check(lib().scht_query_sharded_device(index._h, self._c, q_ptr, nq, dim, K, idx_ptr, d2_ptr, dist_ptr, stream,
+                                               C.byref(stats) if stats is not None else None))
+
+    def close(self):
+        if self._c:
+            lib().scht_comm_destroy(self._c)
+            self._c = C.c_void_p()
 
 
 # ---- data-set files and log text (include/scht.h "Data-set files", "Experiment-log surface") ----------------------

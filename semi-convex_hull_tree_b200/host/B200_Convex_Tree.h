@@ -74,6 +74,22 @@ public:
             throw std::runtime_error("scht_create: " + msg);  // no GPU => no tree: this back-end has no CPU fallback
         }
     }
+    // several GPUs behind the same interface (scht_create_multi): `devices` = CUDA ordinals (empty = every visible GPU),
+    // mode = SCHT_SHARD_QUERIES (tree replicated, each GPU answers a slice of the queries of a call) or SCHT_SHARD_DATASET
+    // (each GPU holds 1/n of the leaves and scans it for all queries; the K-lists are merged over NVLink)
+    B200_Convex_Tree(Matrix<T>& data, float leaf_pts_percent, const std::vector<int>& devices, int mode,
+                     int alg_type = USE_B200_LEAF_APPRXIMATE_QP, unsigned rand_seed = 1)
+        : ALG_TYPE(alg_type), dim_((int)data.ncols()), pct_(leaf_pts_percent) {
+        if (leaf_pts_percent <= 0 || leaf_pts_percent >= 0.5f) throw std::runtime_error("illegal percent, it should be in (0,0.5)");
+        if (scht_build_tree(data.get_matrix_raw_data(), data.nrows(), (int32_t)data.ncols(), leaf_pts_percent, rand_seed, &host_) != SCHT_OK)
+            throw std::runtime_error(std::string("scht_build_tree: ") + scht_last_error());
+        if (scht_create_multi(scht_host_tree_desc(host_), devices.empty() ? nullptr : devices.data(), (int32_t)devices.size(), mode, &dev_) != SCHT_OK) {
+            std::string msg = scht_last_error();
+            scht_host_tree_free(host_);
+            host_ = nullptr;
+            throw std::runtime_error("scht_create_multi: " + msg);
+        }
+    }
     ~B200_Convex_Tree() {
         scht_destroy(dev_);
         scht_host_tree_free(host_);

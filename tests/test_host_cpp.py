@@ -60,3 +60,29 @@ def test_dropin_subclass_with_reference_host_tree(pkg, orc, golden, brute):
     assert_bit_equal(out["idx"].reshape(nq, K), want_idx, "idx")
     assert_bit_equal(out["dist2"].reshape(nq, K), want_d2, "dist2")
     assert_bit_equal(out["dist"].reshape(nq, K), want_d, "dist")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_dropin_subclass_multi_gpu(pkg, orc, mode):
+    """the drop-in with a device list (every visible GPU, at most 4): Convex_Tree<float>::kNN() drives them all from one C++
+    process (mode 0 = queries sharded, 1 = data set sharded); a repeated call replaces the results; same bits as the oracle"""
+    if not os.path.exists(DROPIN_BIN):
+        pytest.skip("oracle/_ref/ref_b200_knn not built (needs the reference sources at build time)")
+    from conftest import load_golden
+    from io_formats import read_records, write_fmat
+    golden = load_golden("uniform16")
+    K, nq = golden["K"], len(golden["queries"])
+    n_gpus = min(4, pkg.lib().scht_device_count())
+    with tempfile.TemporaryDirectory() as td:
+        dp, qp, op = [os.path.join(td, n) for n in ("d.fmat", "q.fmat", "o.knn")]
+        write_fmat(dp, golden["data"])
+        write_fmat(qp, golden["queries"])
+        r = subprocess.run([DROPIN_BIN, dp, repr(golden["pct"]), str(golden["seed"]), qp, str(K), "0", op, str(n_gpus), str(mode), "2"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "call_ms=" in r.stderr
+        out = read_records(op)
+    assert_bit_equal(out["idx"].reshape(nq, K), golden["alg2_idx"], "idx")
+    assert_bit_equal(out["dist2"].reshape(nq, K), golden["alg2_dist2"], "dist2")
+    assert_bit_equal(out["dist"].reshape(nq, K), golden["alg2_dist"], "dist")
