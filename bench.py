@@ -238,7 +238,7 @@ def main():
     arr = ht.arrays()
     tree_info = {"n_leaves": int(arr["n_leaves"]), "tree_depth": int(arr["depth"]), "device_build_s": round(t_build, 2),
                  "device_create_s": round(t_create, 2), "device_tree_MB": info["device_bytes"] >> 20, "scan_groups": lay["scan_groups"],
-                 "scan_pages": lay["scan_pages"]}
+                 "super_groups": lay["super_groups"], "scan_pages": lay["scan_pages"]}
 
     # device-resident leg
     dq = torch.from_numpy(queries).to(dev)

@@ -263,10 +263,11 @@ int scht_query_sharded_device(scht_handle* h, scht_comm* c, const float* d_queri
 /* Tree facts of a handle (for logs: print_tree_info, Code/Convex_Tree.h:946-958). */
 int scht_handle_info(const scht_handle* h, int32_t* dim, int64_t* n_points, int32_t* n_nodes, int32_t* n_leaves,
                      int32_t* device, int64_t* device_bytes);
-/* Device layout facts: devices behind the handle, sharding mode, scan groups / scan pages of the prefilter image of the
- * first device (0 when it was not built) and the leaves resident there.  Any pointer may be NULL. */
+/* Device layout facts: devices behind the handle, sharding mode, k-means groups / super-groups / scan pages (padding
+ * included) of the prefilter image of the first device (0 when it was not built) and the leaves resident there.  Any
+ * pointer may be NULL. */
 int scht_handle_layout(const scht_handle* h, int32_t* n_devices, int32_t* mode, int32_t* n_scan_groups,
-                       int64_t* n_scan_pages, int32_t* leaf_begin, int32_t* leaf_end);
+                       int32_t* n_super_groups, int64_t* n_scan_pages, int32_t* leaf_begin, int32_t* leaf_end);
 
 /* ------------------------------------------------------------------------------------------------
  * Data-set files.  Replaces read_data / read_data_dim_size / get_dim / get_data

@@ -87,7 +87,7 @@ SYMBOLS = {
     "scht_comm_query_slice": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "scht_query_sharded_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
-    "scht_handle_layout": (C.c_int, [C.c_void_p, i32p, i32p, i32p, C.POINTER(C.c_int64), i32p, i32p]),
+    "scht_handle_layout": (C.c_int, [C.c_void_p, i32p, i32p, i32p, i32p, C.POINTER(C.c_int64), i32p, i32p]),
     "scht_read_text": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(f32p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "scht_write_text": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
     "scht_write_bin": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
@@ -255,10 +255,11 @@ class Index:
         return v.value
 
     def layout(self):
-        nd, mode, ng, lb, le = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        nd, mode, ng, ns, lb, le = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         npg = C.c_int64()
-        _check(lib().scht_handle_layout(self._h, C.byref(nd), C.byref(mode), C.byref(ng), C.byref(npg), C.byref(lb), C.byref(le)))
-        return dict(n_devices=nd.value, mode=mode.value, scan_groups=ng.value, scan_pages=npg.value, leaf_begin=lb.value, leaf_end=le.value)
+        _check(lib().scht_handle_layout(self._h, C.byref(nd), C.byref(mode), C.byref(ng), C.byref(ns), C.byref(npg), C.byref(lb), C.byref(le)))
+        return dict(n_devices=nd.value, mode=mode.value, scan_groups=ng.value, super_groups=ns.value, scan_pages=npg.value,
+                    leaf_begin=lb.value, leaf_end=le.value)
 
     def set_batch_size(self, n):
         _check(lib().scht_set_batch_size(self._h, int(n)))

@@ -204,13 +204,27 @@ __global__ void __launch_bounds__(256) k_group_means(DevTree T, const unsigned l
     }
 }
 
-__global__ void k_slot_pos(const unsigned long long* __restrict__ keys, int n, int n_slots_padded, int* __restrict__ slot_pos) {
+// key (old group, position) -> key (order index of the group, position)
+__global__ void k_remap_keys(const unsigned long long* __restrict__ in, int n, const int* __restrict__ newid, unsigned long long* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_slots_padded) slot_pos[i] = (i < n) ? (int)(unsigned int)keys[i] : -1;
+    if (i < n) out[i] = ((unsigned long long)(unsigned int)newid[(int)(in[i] >> 32)] << 32) | (unsigned int)in[i];
+}
+// sorted keys -> slots: member i of group g goes to goff[g] + (i - gstart[g]); slot_pos was filled with -1 (padding)
+__global__ void k_scatter_slots(const unsigned long long* __restrict__ keys, int n, const int* __restrict__ gstart, const int* __restrict__ goff,
+                                int* __restrict__ slot_pos) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = (int)(keys[i] >> 32);
+    slot_pos[goff[g] + ((int)i - gstart[g])] = (int)(unsigned int)keys[i];
+}
+__global__ void k_iota_slots(int first, int n, int n_slots, int* __restrict__ slot_pos) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slots) slot_pos[i] = (i < n) ? first + (int)i : -1;
 }
 
-// bounding ball of every scan page: centre = mean of its points, radius = max distance (rounded up, ball_eps)
-__global__ void __launch_bounds__(256) k_page_balls(DevTree T, const int* __restrict__ slot_pos, float* __restrict__ pcen, float* __restrict__ prad) {
+// bounding ball of every scan page: centre = mean of its points, radius = max distance (rounded up, ball_eps); pcnt = points
+__global__ void __launch_bounds__(256) k_page_balls(DevTree T, const int* __restrict__ slot_pos, float* __restrict__ pcen, float* __restrict__ prad,
+                                                    int* __restrict__ pcnt) {
     extern __shared__ float cen_s[];  // [dpad]
     __shared__ float red[8];
     const int sp = blockIdx.x;
@@ -233,19 +247,41 @@ __global__ void __launch_bounds__(256) k_page_balls(DevTree T, const int* __rest
             d2 = fmaf(d, d, d2);
         }
     const float m = block_max(d2, red);
-    if (threadIdx.x == 0) prad[sp] = sqrtf(m) * (1.f + ball_eps(T.dim)) + 1e-37f;
+    if (threadIdx.x == 0) {
+        prad[sp] = sqrtf(m) * (1.f + ball_eps(T.dim)) + 1e-37f;
+        pcnt[sp] = (int)cnt;
+    }
 }
 
-__global__ void __launch_bounds__(256) k_group_balls(DevTree T, const int* __restrict__ slot_pos, const int* __restrict__ gslot, const float* __restrict__ gcen,
-                                                     float* __restrict__ grad) {
+// bounding ball of a run of slots [first[b], first[b+1]) * unit (unit = 256: super-groups given by page boundaries)
+// centre: mean of the points of the run
+__global__ void __launch_bounds__(256) k_run_balls(DevTree T, const int* __restrict__ slot_pos, const int* __restrict__ first, int unit, float* __restrict__ cen,
+                                                   float* __restrict__ rad) {
     extern __shared__ float cen_s[];  // [dpad]
     __shared__ float red[8];
-    const int g = blockIdx.x, b = gslot[g], e = gslot[g + 1];
-    for (int j = threadIdx.x; j < T.dpad; j += blockDim.x) cen_s[j] = gcen[(size_t)g * T.dpad + j];
+    const int g = blockIdx.x;
+    const long long b = (long long)first[g] * unit, e = (long long)first[g + 1] * unit;
+    float cnt = 0.f;
+    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) cnt += slot_pos[i] >= 0 ? 1.f : 0.f;
+    cnt = block_sum(cnt, red);
+    for (int j = 0; j < T.dpad; j++) {
+        float s = 0.f;
+        for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+            const int pos = slot_pos[i];
+            if (pos >= 0) s += page_coord(T, pos, j);
+        }
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) {
+            const float c = s / fmaxf(cnt, 1.f);
+            cen_s[j] = c;
+            cen[(size_t)g * T.dpad + j] = c;
+        }
+    }
     __syncthreads();
     float m = 0.f;
-    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
         const int pos = slot_pos[i];
+        if (pos < 0) continue;
         float d2 = 0.f;
         for (int j = 0; j < T.dpad; j++) {
             const float d = page_coord(T, pos, j) - cen_s[j];
@@ -254,7 +290,29 @@ __global__ void __launch_bounds__(256) k_group_balls(DevTree T, const int* __res
         m = fmaxf(m, d2);
     }
     m = block_max(m, red);
-    if (threadIdx.x == 0) grad[g] = sqrtf(m) * (1.f + ball_eps(T.dim)) + 1e-37f;
+    if (threadIdx.x == 0) rad[g] = sqrtf(m) * (1.f + ball_eps(T.dim)) + 1e-37f;
+}
+
+// radius of every k-means group around its centroid (members = sorted keys [gslot[g], gslot[g+1]))
+__global__ void __launch_bounds__(256) k_group_radii(DevTree T, const unsigned long long* __restrict__ keys, const int* __restrict__ gslot,
+                                                     const float* __restrict__ gcen, float* __restrict__ grad) {
+    extern __shared__ float cen_s[];  // [dpad]
+    __shared__ float red[8];
+    const int g = blockIdx.x, b = gslot[g], e = gslot[g + 1];
+    for (int j = threadIdx.x; j < T.dpad; j += blockDim.x) cen_s[j] = gcen[(size_t)g * T.dpad + j];
+    __syncthreads();
+    float m = 0.f;
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const int pos = (int)(unsigned int)keys[i];
+        float d2 = 0.f;
+        for (int j = 0; j < T.dpad; j++) {
+            const float d = page_coord(T, pos, j) - cen_s[j];
+            d2 = fmaf(d, d, d2);
+        }
+        m = fmaxf(m, d2);
+    }
+    m = block_max(m, red);
+    if (threadIdx.x == 0) grad[g] = sqrtf(m);
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -332,6 +390,77 @@ __global__ void __launch_bounds__(256) k_sample_mean(DevTree T, int ns, float* _
         if (rc__) return rc__;            \
     } while (0)
 
+// Order of the k-means groups: recursive bisection of their centroids (two far-apart pivots, every centroid to the nearer
+// one -- the split rule of the tree itself, Code/Convex_Tree.h:789-821, applied to a few thousand centroids on the host), read
+// off depth first: neighbours in the order are neighbours in space.  Empty groups are left out.
+void order_groups(const std::vector<float>& cen, int dpad, const std::vector<int>& size, std::vector<int>& order) {
+    std::vector<int> ids;
+    for (int g = 0; g < (int)size.size(); g++)
+        if (size[g] > 0) ids.push_back(g);
+    order.clear();
+    order.reserve(ids.size());
+    auto dist2 = [&](int a, const double* m) {
+        double s = 0;
+        const float* p = &cen[(size_t)a * dpad];
+        for (int j = 0; j < dpad; j++) {
+            const double d = (double)p[j] - m[j];
+            s += d * d;
+        }
+        return s;
+    };
+    auto dist2g = [&](int a, int b) {
+        double s = 0;
+        const float *p = &cen[(size_t)a * dpad], *q = &cen[(size_t)b * dpad];
+        for (int j = 0; j < dpad; j++) {
+            const double d = (double)p[j] - (double)q[j];
+            s += d * d;
+        }
+        return s;
+    };
+    std::vector<std::pair<int, int>> stack;  // ranges [b, e) of ids still to split (processed right to left so the order is DFS)
+    stack.emplace_back(0, (int)ids.size());
+    std::vector<double> mean(dpad);
+    std::vector<int> tmp;
+    while (!stack.empty()) {
+        const int b = stack.back().first, e = stack.back().second;
+        stack.pop_back();
+        if (e - b <= 1) {
+            if (e > b) order.push_back(ids[b]);
+            continue;
+        }
+        std::fill(mean.begin(), mean.end(), 0.0);
+        for (int i = b; i < e; i++)
+            for (int j = 0; j < dpad; j++) mean[j] += cen[(size_t)ids[i] * dpad + j];
+        for (int j = 0; j < dpad; j++) mean[j] /= (e - b);
+        int pa = b, pb = b;
+        double best = -1;
+        for (int i = b; i < e; i++) {
+            const double d = dist2(ids[i], mean.data());
+            if (d > best) best = d, pa = i;
+        }
+        best = -1;
+        for (int i = b; i < e; i++) {
+            const double d = dist2g(ids[i], ids[pa]);
+            if (d > best) best = d, pb = i;
+        }
+        const int ga = ids[pa], gb = ids[pb];
+        tmp.clear();
+        int w = b;
+        for (int i = b; i < e; i++) {
+            if (dist2g(ids[i], ga) <= dist2g(ids[i], gb)) ids[w++] = ids[i];
+            else tmp.push_back(ids[i]);
+        }
+        if (w == b || w == e) {  // all centroids coincide: keep them as they are
+            for (size_t k = 0; k < tmp.size(); k++) ids[w + k] = tmp[k];
+            for (int i = b; i < e; i++) order.push_back(ids[i]);
+            continue;
+        }
+        for (size_t k = 0; k < tmp.size(); k++) ids[w + k] = tmp[k];
+        stack.emplace_back(w, e);  // right half later
+        stack.emplace_back(b, w);  // left half first
+    }
+}
+
 // ---- the scan-order image (ScanImage) of the resident points -----------------------------------------------
 int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<float>& pmax_h, double n2max, const float* leaf_means) {
     DevTree& T = h->T;
@@ -340,11 +469,9 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
     const int dim = T.dim, dpad = T.dpad;
     const int n = T.pos_hi - T.pos_lo;
     const int kp = (dim + 3 + 15) & ~15;
-    const int n_spages = (n + kPage - 1) / kPage;
-    const size_t tbytes = (size_t)n_spages * tc_page_bytes(kp);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    if (tbytes + (size_t)n * 24 >= free_b / 2) return SCHT_OK;  // no room for the image: the exact FP32 scan serves every batch
+    if ((size_t)((double)n * 1.1 / kPage + 2) * tc_page_bytes(kp) + (size_t)n * 28 >= free_b / 2) return SCHT_OK;  // no room for the image: the exact FP32 scan serves every batch
 
     double amax_all = 0, asum = 0;
     for (int j = 0; j < dim; j++) {
@@ -361,21 +488,21 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
     // s^2 must stay a normal float in the filter bound (k_scan_tc::bound_of): 2^-60 <= s <= 2^60
     if (!(std::isfinite(I.pnorm_max) && std::isfinite(I.scale) && I.scale >= 8.6736174e-19f && I.scale <= 1.1529215e18f && sn < 1e37)) return SCHT_OK;
 
-    // ---- scan groups ----
+    // ---- k-means groups (build-time only): ~512 points each ----
     int C = h->opt.groups;
-    if (C < 0) C = (n < 8192) ? 1 : std::min(8192, n / 2048);
+    if (C < 0) C = (n < 8192) ? 1 : std::min(32768, n / 512);
     C = std::max(1, std::min(C, std::max(1, n / kPage)));
     unsigned long long *keys_a = nullptr, *keys_b = nullptr;
-    int* grp = nullptr;
+    int *grp = nullptr, *d_newid = nullptr, *d_gstart = nullptr, *d_goff = nullptr;
+    float *d_gcen = nullptr, *d_grad = nullptr, *d_lm = nullptr;
+    int* d_lg = nullptr;
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
     int end_bit = 32;
     for (int c = C - 1; c > 0; c >>= 1) end_bit++;
     auto free_tmp = [&]() {
-        if (keys_a) cudaFree(keys_a);
-        if (keys_b) cudaFree(keys_b);
-        if (grp) cudaFree(grp);
-        if (cub_tmp) cudaFree(cub_tmp);
+        for (void* p : {(void*)keys_a, (void*)keys_b, (void*)grp, (void*)d_newid, (void*)d_gstart, (void*)d_goff, (void*)d_gcen, (void*)d_grad, (void*)d_lm, (void*)d_lg, cub_tmp})
+            if (p) cudaFree(p);
     };
 #define CU_T(expr)                                                                                          \
     do {                                                                                                     \
@@ -386,71 +513,143 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
                               std::string(#expr) + ": " + cudaGetErrorString(e__));                         \
         }                                                                                                    \
     } while (0)
-    CU_T(cudaMalloc(&keys_a, (size_t)n * 8));
-    float* gcen = nullptr;
-    TRY_H(dev_alloc(h, (size_t)C * dpad, &gcen));
-    int* gslot = nullptr;
-    TRY_H(dev_alloc(h, (size_t)C + 1, &gslot));
-    const unsigned long long* keys = keys_a;
+#define TRY_T(x)            \
+    do {                    \
+        int rc__ = (x);     \
+        if (rc__) {         \
+            free_tmp();     \
+            return rc__;    \
+        }                   \
+    } while (0)
     const unsigned nb = (unsigned)((n + 255) / 256);
+    std::vector<int> goff_h, spage_h;   // slot offset of every ordered group; first page of every super-group
+    std::vector<float> cen_ord;         // centroids in scan order (bucket order of the leaves)
+    int n_spages = (n + kPage - 1) / kPage;
+    std::vector<char> hard;             // hard[p]: a page break (padding) ends right before page p
+    int* slot_pos = nullptr;
     if (C > 1) {
+        CU_T(cudaMalloc(&keys_a, (size_t)n * 8));
         CU_T(cudaMalloc(&keys_b, (size_t)n * 8));
         CU_T(cudaMalloc(&grp, (size_t)n * 4));
+        CU_T(cudaMalloc(&d_gcen, (size_t)C * dpad * 4));
+        CU_T(cudaMalloc(&d_grad, (size_t)C * 4));
+        CU_T(cudaMalloc(&d_gstart, (size_t)(C + 1) * 4));
+        CU_T(cudaMalloc(&d_goff, (size_t)(C + 1) * 4));
+        CU_T(cudaMalloc(&d_newid, (size_t)C * 4));
         CU_T(cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, keys_a, keys_b, n, 0, end_bit, s));
         CU_T(cudaMalloc(&cub_tmp, std::max<size_t>(cub_bytes, 16)));
-        k_gather_seeds<<<(unsigned)(((size_t)C * dpad + 255) / 256), 256, 0, s>>>(T, C, gcen);
+        k_gather_seeds<<<(unsigned)(((size_t)C * dpad + 255) / 256), 256, 0, s>>>(T, C, d_gcen);
         for (int it = 0; it < 2; it++) {  // assign -> sort by (group, position) -> centroids = member means
-            k_assign<false><<<nb, 256, 0, s>>>(T, nullptr, T.pos_lo, n, gcen, C, grp);
+            k_assign<false><<<nb, 256, 0, s>>>(T, nullptr, T.pos_lo, n, d_gcen, C, grp);
             k_make_keys<<<nb, 256, 0, s>>>(grp, T.pos_lo, n, keys_a);
             CU_T(cub::DeviceRadixSort::SortKeys(cub_tmp, cub_bytes, keys_a, keys_b, n, 0, end_bit, s));
-            k_group_bounds<<<(C + 1 + 255) / 256, 256, 0, s>>>(keys_b, n, C, gslot);
-            k_group_means<<<C, 256, 0, s>>>(T, keys_b, gslot, gcen);
+            k_group_bounds<<<(C + 1 + 255) / 256, 256, 0, s>>>(keys_b, n, C, d_gstart);
+            k_group_means<<<C, 256, 0, s>>>(T, keys_b, d_gstart, d_gcen);
             CU_T(cudaGetLastError());
         }
-        keys = keys_b;
+        k_group_radii<<<C, 256, dpad * sizeof(float), s>>>(T, keys_b, d_gstart, d_gcen, d_grad);
+        std::vector<float> cen_h((size_t)C * dpad), rad_h(C);
+        std::vector<int> gstart_h(C + 1), size_h(C);
+        CU_T(cudaMemcpyAsync(cen_h.data(), d_gcen, cen_h.size() * 4, cudaMemcpyDeviceToHost, s));
+        CU_T(cudaMemcpyAsync(rad_h.data(), d_grad, rad_h.size() * 4, cudaMemcpyDeviceToHost, s));
+        CU_T(cudaMemcpyAsync(gstart_h.data(), d_gstart, gstart_h.size() * 4, cudaMemcpyDeviceToHost, s));
+        CU_T(cudaStreamSynchronize(s));
+        for (int g = 0; g < C; g++) size_h[g] = gstart_h[g + 1] - gstart_h[g];
+        // ---- host: order of the groups, page breaks, super-groups ----
+        std::vector<int> order;
+        order_groups(cen_h, dpad, size_h, order);
+        const int Cn = (int)order.size();
+        std::vector<int> newid(C, 0);
+        for (int i = 0; i < Cn; i++) newid[order[i]] = i;
+        // a page break after group i when empty space separates it from group i+1 (gap between the two balls larger than half
+        // the bigger radius): the padding keeps a page from straddling two clusters.  Widest gaps first, at most 8 % padding.
+        std::vector<std::pair<double, int>> cand;
+        for (int i = 0; i + 1 < Cn; i++) {
+            const int a = order[i], b = order[i + 1];
+            double d2 = 0;
+            for (int j = 0; j < dpad; j++) {
+                const double d = (double)cen_h[(size_t)a * dpad + j] - (double)cen_h[(size_t)b * dpad + j];
+                d2 += d * d;
+            }
+            const double gap = std::sqrt(d2) - rad_h[a] - rad_h[b];
+            if (gap > 0.5 * std::max(rad_h[a], rad_h[b])) cand.emplace_back(gap, i);
+        }
+        std::sort(cand.begin(), cand.end(), [](const std::pair<double, int>& x, const std::pair<double, int>& y) { return x.first > y.first; });
+        const size_t max_breaks = (size_t)((double)n * 0.08 / (kPage / 2));
+        std::vector<char> brk(Cn, 0);
+        for (size_t k = 0; k < cand.size() && k < max_breaks; k++) brk[cand[k].second] = 1;
+        goff_h.assign(Cn + 1, 0);
+        long long off = 0;
+        std::vector<long long> hard_slots;
+        for (int i = 0; i < Cn; i++) {
+            goff_h[i] = (int)off;
+            off += size_h[order[i]];
+            if (brk[i]) {
+                off = (off + kPage - 1) / kPage * kPage;
+                hard_slots.push_back(off);
+            }
+        }
+        goff_h[Cn] = (int)off;
+        n_spages = (int)((off + kPage - 1) / kPage);
+        hard.assign(n_spages + 1, 0);
+        for (long long x : hard_slots)
+            if (x / kPage <= n_spages) hard[x / kPage] = 1;
+        cen_ord.resize((size_t)Cn * dpad);
+        for (int i = 0; i < Cn; i++) memcpy(&cen_ord[(size_t)i * dpad], &cen_h[(size_t)order[i] * dpad], sizeof(float) * dpad);
+        // ---- device: keys by (order index, position) -> slots ----
+        CU_T(cudaMemcpyAsync(d_newid, newid.data(), (size_t)C * 4, cudaMemcpyHostToDevice, s));
+        CU_T(cudaMemcpyAsync(d_goff, goff_h.data(), (size_t)(Cn + 1) * 4, cudaMemcpyHostToDevice, s));
+        k_remap_keys<<<nb, 256, 0, s>>>(keys_b, n, d_newid, keys_a);
+        CU_T(cub::DeviceRadixSort::SortKeys(cub_tmp, cub_bytes, keys_a, keys_b, n, 0, end_bit, s));
+        k_group_bounds<<<(Cn + 1 + 255) / 256, 256, 0, s>>>(keys_b, n, Cn, d_gstart);
+        TRY_T(dev_alloc(h, (size_t)n_spages * kPage, &slot_pos));
+        CU_T(cudaMemsetAsync(slot_pos, 0xff, (size_t)n_spages * kPage * 4, s));
+        k_scatter_slots<<<nb, 256, 0, s>>>(keys_b, n, d_gstart, d_goff, slot_pos);
+        CU_T(cudaGetLastError());
     } else {
-        k_make_keys<<<nb, 256, 0, s>>>(nullptr, T.pos_lo, n, keys_a);  // one group: tree order
-        k_group_bounds<<<1, 256, 0, s>>>(keys_a, n, C, gslot);
-        k_group_means<<<C, 256, 0, s>>>(T, keys_a, gslot, gcen);
+        hard.assign(n_spages + 1, 0);
+        TRY_T(dev_alloc(h, (size_t)n_spages * kPage, &slot_pos));
+        k_iota_slots<<<(unsigned)(((size_t)n_spages * kPage + 255) / 256), 256, 0, s>>>(T.pos_lo, n, n_spages * kPage, slot_pos);  // one group: tree order
         CU_T(cudaGetLastError());
     }
-    int* slot_pos = nullptr;
-    float *pcen = nullptr, *prad = nullptr, *grad = nullptr;
+    // super-groups: runs of <= kSuperPages pages that do not cross a page break
+    spage_h.push_back(0);
+    for (int p = 1; p <= n_spages; p++)
+        if (p == n_spages || hard[p] || p - spage_h.back() >= kSuperPages) spage_h.push_back(p);
+    const int S = (int)spage_h.size() - 1;
+
+    float *pcen = nullptr, *prad = nullptr, *scen = nullptr, *srad = nullptr;
+    int *pcnt = nullptr, *spage = nullptr;
     unsigned char* tcp = nullptr;
-    TRY_H(dev_alloc(h, (size_t)n_spages * kPage, &slot_pos));
-    TRY_H(dev_alloc(h, (size_t)n_spages * dpad, &pcen));
-    TRY_H(dev_alloc(h, (size_t)n_spages, &prad));
-    TRY_H(dev_alloc(h, (size_t)C, &grad));
-    TRY_H(dev_alloc(h, tbytes, &tcp));
-    k_slot_pos<<<(unsigned)(((size_t)n_spages * kPage + 255) / 256), 256, 0, s>>>(keys, n, n_spages * kPage, slot_pos);
+    TRY_T(dev_alloc(h, (size_t)n_spages * dpad, &pcen));
+    TRY_T(dev_alloc(h, (size_t)n_spages, &prad));
+    TRY_T(dev_alloc(h, (size_t)n_spages, &pcnt));
+    TRY_T(dev_alloc(h, (size_t)S * dpad, &scen));
+    TRY_T(dev_alloc(h, (size_t)S, &srad));
+    TRY_T(dev_alloc(h, (size_t)S + 1, &spage));
+    TRY_T(dev_alloc(h, (size_t)n_spages * tc_page_bytes(kp), &tcp));
+    CU_T(cudaMemcpyAsync(spage, spage_h.data(), (size_t)(S + 1) * 4, cudaMemcpyHostToDevice, s));
     k_build_tcpages<<<(unsigned)(((size_t)n_spages * kPage + 255) / 256), 256, 0, s>>>(T, slot_pos, n_spages, d_mean, I.scale, I.norm_unit, kp, tcp);
-    k_page_balls<<<n_spages, 256, dpad * sizeof(float), s>>>(T, slot_pos, pcen, prad);
-    k_group_balls<<<C, 256, dpad * sizeof(float), s>>>(T, slot_pos, gslot, gcen, grad);
+    k_page_balls<<<n_spages, 256, dpad * sizeof(float), s>>>(T, slot_pos, pcen, prad, pcnt);
+    k_run_balls<<<S, 256, dpad * sizeof(float), s>>>(T, slot_pos, spage, kPage, scen, srad);
     CU_T(cudaGetLastError());
 
-    // ---- bucket order of the leaves: by (scan group nearest to the leaf's mean, leaf id), so that the queries of a tile
-    // (bucketed by approximate leaf) want the same scan pages ----
+    // ---- bucket order of the leaves: by (ordered scan group nearest to the leaf's mean, leaf id), so that the queries of a
+    // tile (bucketed by approximate leaf) want the same scan pages ----
     std::vector<int> rank(T.n_leaves);
     std::iota(rank.begin(), rank.end(), 0);
-    if (C > 1 && leaf_means) {
-        float* d_lm = nullptr;
-        int* d_lg = nullptr;
+    if (C > 1 && leaf_means && !cen_ord.empty()) {
+        const int Cn = (int)(cen_ord.size() / dpad);
         std::vector<float> lm((size_t)T.n_leaves * dpad, 0.f);
         for (int l = 0; l < T.n_leaves; l++) memcpy(&lm[(size_t)l * dpad], leaf_means + (size_t)l * dim, sizeof(float) * dim);
         CU_T(cudaMalloc(&d_lm, lm.size() * 4));
-        cudaError_t e2 = cudaMalloc(&d_lg, (size_t)T.n_leaves * 4);
-        if (e2 != cudaSuccess) {
-            cudaFree(d_lm);
-            CU_T(e2);
-        }
-        cudaMemcpyAsync(d_lm, lm.data(), lm.size() * 4, cudaMemcpyHostToDevice, s);
-        k_assign<true><<<(T.n_leaves + 255) / 256, 256, 0, s>>>(T, d_lm, 0, T.n_leaves, gcen, C, d_lg);
+        CU_T(cudaMalloc(&d_lg, (size_t)T.n_leaves * 4));
+        CU_T(cudaMemcpyAsync(d_lm, lm.data(), lm.size() * 4, cudaMemcpyHostToDevice, s));
+        CU_T(cudaMemcpyAsync(d_gcen, cen_ord.data(), cen_ord.size() * 4, cudaMemcpyHostToDevice, s));
+        k_assign<true><<<(T.n_leaves + 255) / 256, 256, 0, s>>>(T, d_lm, 0, T.n_leaves, d_gcen, Cn, d_lg);
         std::vector<int> lg(T.n_leaves);
-        cudaMemcpyAsync(lg.data(), d_lg, (size_t)T.n_leaves * 4, cudaMemcpyDeviceToHost, s);
-        cudaError_t e3 = cudaStreamSynchronize(s);
-        cudaFree(d_lm);
-        cudaFree(d_lg);
-        CU_T(e3);
+        CU_T(cudaMemcpyAsync(lg.data(), d_lg, (size_t)T.n_leaves * 4, cudaMemcpyDeviceToHost, s));
+        CU_T(cudaStreamSynchronize(s));
         std::vector<int> order(T.n_leaves);
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lg[a] < lg[b]; });
@@ -459,16 +658,19 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
     CU_T(cudaStreamSynchronize(s));
     free_tmp();
 #undef CU_T
+#undef TRY_T
     CU_TRY(cudaMemcpy(const_cast<int*>(T.leaf_rank), rank.data(), (size_t)T.n_leaves * 4, cudaMemcpyHostToDevice));
     I.tcpages = tcp;
     I.slot_pos = slot_pos;
+    I.pcnt = pcnt;
     I.pcen = pcen;
     I.prad = prad;
-    I.gcen = gcen;
-    I.grad = grad;
-    I.gslot = gslot;
-    I.n_slots = n;
+    I.scen = scen;
+    I.srad = srad;
+    I.spage = spage;
+    I.n_slots = n_spages * kPage;
     I.n_spages = n_spages;
+    I.n_supers = S;
     I.n_groups = C;
     I.mean = d_mean;
     I.kp = kp;

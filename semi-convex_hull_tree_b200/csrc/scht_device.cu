@@ -285,12 +285,80 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
     const int page_hi = use_tc ? I.n_spages : (P.pos_hi + kPage - 1) / kPage;
     const int n_list_pages = std::max(1, page_hi - page_lo);
     bool pruned = false;  // the page lists are (much) shorter than "every page"
+
+    // ---- the prefilter scan kernel over the current page lists (used for the first pass of a pruned batch and for the main scan)
+    auto launch_tc_scan = [&](int write_mode, bool allow_split) -> int {
+        TcScanParams TC{};
+        TC.S = P;
+        TC.S.mode = kScanList;
+        TC.S.write_mode = write_mode;
+        TC.S.range_groups = kMaxCuts;
+        TC.I = I;
+        TC.brute = brute ? 1 : 0;
+        TC.n_stages = tc_stages;
+        // Tail effect: n_tiles CTAs of equal length on n_sm SMs take ceil(n_tiles/n_sm) rounds (782 tiles on 148 SMs: 6 rounds
+        // for 5.28 rounds of work).  Splitting every tile's page list into S segments (own CTA each, partial lists merged by
+        // k_merge_partial) makes the rounds S times shorter: pick the S <= 8 with the smallest ceil(S*n_tiles/n_sm)/S, charging
+        // 5 % per extra segment for the repeated set-up and the looser early bounds (measured).  Also what keeps a SMALL batch from
+        // running on a handful of SMs.  Not with pruned page lists: their pages are not spread over the page index range.
+        int n_seg = 1;
+        if (allow_split && write_mode == kWriteFinal && h->opt.tc_split && !(pruned && h->opt.tc_split == 1 && n_tiles_main >= h->n_sm)) {
+            double best = 1e30;
+            for (int S = 1; S <= 8; S++) {
+                if (S > 1 && (page_hi - page_lo) / S < 64) break;
+                const double rounds = std::ceil((double)S * n_tiles_main / h->n_sm) / S * (1.0 + 0.05 * (S - 1));
+                if (rounds < best - 1e-9) {
+                    best = rounds;
+                    n_seg = S;
+                }
+            }
+            if (h->opt.tc_split > 1) n_seg = std::min(8, h->opt.tc_split);  // forced
+            if (n_seg > 1) {
+                CU_TRY(h->seg_keys.reserve((size_t)n_seg * nq * K * sizeof(uint64_t)));
+                TC.S.keys_out = h->seg_keys.as<uint64_t>();
+                TC.S.n_slices = 0;
+                TC.seg_page0 = page_lo;
+                TC.seg_pages = (page_hi - page_lo + n_seg - 1) / n_seg;
+            }
+        }
+        TC.n_seg = n_seg;
+        size_t smem = tc_smem_bytes(T.dpad, I.kp, K, tc_stages);
+        // One K slice per page (narrow points): two issuers, one per page parity, each issuing the page's two N=128 half-page
+        // chains (+3 % over four issuers; whole-page N=256 chains cost 2.4 % there).  Several slices per page (wide points): the
+        // MMA time counts, and one N=256 chain per page (128 instead of 2 x 92 cycles per K16 step) beats four issuers of
+        // half-page chains by 2 % (D=128) to 5 % (D=32).
+        const bool wide = I.kp > kTcKSlice;
+        bool want_n256 = (h->opt.tc_n256 < 0) ? wide : (h->opt.tc_n256 != 0);
+        int n_iss = (wide && !want_n256) ? 4 : 2;
+        if (h->opt.tc_issuers == 2 || h->opt.tc_issuers == 4) n_iss = h->opt.tc_issuers;
+        auto launch_tc = [&](auto kernel, int threads) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) kernel<<<n_tiles_main * n_seg, threads, smem, s>>>(TC);
+            return e;
+        };
+        const bool rows = T.rows != nullptr;  // wide points: exact re-evaluation from the row-major copy
+        const bool n256 = n_iss == 2 && want_n256;
+        if (n256) CU_TRY(rows ? launch_tc(k_scan_tc<2, true, true>, tc_threads(2)) : launch_tc(k_scan_tc<2, false, true>, tc_threads(2)));
+        else if (n_iss == 2) CU_TRY(rows ? launch_tc(k_scan_tc<2, true, false>, tc_threads(2)) : launch_tc(k_scan_tc<2, false, false>, tc_threads(2)));
+        else CU_TRY(rows ? launch_tc(k_scan_tc<4, true, false>, tc_threads(4)) : launch_tc(k_scan_tc<4, false, false>, tc_threads(4)));
+        CU_TRY(cudaGetLastError());
+        launches++;
+        scans++;
+        if (n_seg > 1) {
+            k_merge_partial<<<(nq + 127) / 128, 128, 0, s>>>(T, h->seg_keys.as<uint64_t>(), n_seg, nq, K, brute ? 1 : 0, P.idx_out, P.d2_out, P.dist_out);
+            CU_TRY(cudaGetLastError());
+            launches++;
+        }
+        return SCHT_OK;
+    };
+
     if (brute && !use_tc) {
         // exact FP32 exhaustive scan (k_scan walks every resident page itself)
     } else {
         // Which pages does a tile scan?  prefilter scan: ball test of the scan pages (k_select_pages); exact scan: tree traversal
-        // with the hyper-plane bounds (k_traverse).  Sampled first (about 24 tiles, at least every 64th and at most every 8th):
-        // when the bounds keep most pages anyway they are not evaluated for the other tiles (every page is listed).
+        // with the hyper-plane bounds (k_traverse).  Probed first on a sample (about 24 tiles, at least every 64th and at most every
+        // 8th; a small batch: all tiles): when the bounds keep most pages anyway they are not evaluated for the other tiles
+        // (every page is listed).
         const bool can_select = use_tc && h->opt.page_select && select_fits(h);
         SelectParams SP{};
         TraverseParams TP{};
@@ -324,10 +392,12 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             TP.counters = ctr;
             TP.ball_only = 0;
         }
-        auto bounds_pass = [&](int mode, int step) -> int {
+        auto bounds_pass = [&](int mode, int step, int nearest) -> int {
+            launches++;
             if (use_tc) {
                 SP.sel_mode = mode;
                 SP.sel_step = step;
+                SP.nearest = nearest;
                 return launch_select(h, SP, s);
             }
             TP.sel_mode = mode;
@@ -339,45 +409,56 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             if (cnt > 0) k_list_all<<<(cnt + 127) / 128, 128, 0, s>>>(h->ranges.as<int2>(), h->n_ranges.as<int>(), n_tiles_main, use_tc ? kMaxCuts : T.n_cuts, mode, step,
                                                                       page_lo, page_hi);
             CU_TRY(cudaGetLastError());
+            launches++;
             return SCHT_OK;
         };
-        const int kSample = std::max(8, std::min(64, n_tiles_main / 24));
+        const bool sampling = n_tiles_main >= 64 && h->opt.traverse_sampling;
+        const int kSample = sampling ? std::max(8, std::min(64, n_tiles_main / 24)) : 1;
         const long long sig = (long long)use_tc | ((long long)K << 1) | ((long long)P.pos_lo << 12) | ((long long)(brute ? 1 : 0) << 11) | ((long long)P.pos_hi << 36);
         int rc = SCHT_OK;
         if (use_tc && !can_select) {
             rc = list_all(0, 1);
-            launches++;
-        } else if (n_tiles_main >= 64 && h->opt.traverse_sampling && h->sample_skip > 0 && sig == h->sample_sig) {
+        } else if (sampling && h->sample_skip > 0 && sig == h->sample_sig) {
             // the samples of the last batches of this shape all kept (nearly) every page: list them without asking again
             h->sample_skip--;
             rc = list_all(0, 1);
-            launches++;
-        } else if (n_tiles_main >= 64 && h->opt.traverse_sampling) {
+        } else {
+            // probe: the sampled tiles (or all tiles of a small batch)
             unsigned long long listed = 0;
-            rc = bounds_pass(1, kSample);
+            rc = bounds_pass(sampling ? 1 : 0, kSample, 0);
             if (rc) return rc;
-            launches++;
             CU_TRY(cudaMemcpyAsync(&listed, ctr + 5, 8, cudaMemcpyDeviceToHost, s));
             CU_TRY(cudaStreamSynchronize(s));
-            long long sampled_q = 0;
-            for (int t = 0; t < n_tiles_main; t += kSample) sampled_q += std::min(tq_main, nq - t * tq_main);
-            const double kept = (double)listed / std::max(1.0, (double)sampled_q * n_list_pages);
+            long long probed_q = 0;
+            for (int t = 0; t < n_tiles_main; t += kSample) probed_q += std::min(tq_main, nq - t * tq_main);
+            const double kept = (double)listed / std::max(1.0, (double)probed_q * n_list_pages);
             // a prefilter page costs ~1/10 of an exact page, so pruning must remove much more before it pays for itself
-            if (kept >= (use_tc ? 0.60 : 0.90)) {
-                rc = list_all(2, kSample);
-                if (sig != h->sample_sig) h->sample_streak = 0;
-                if (++h->sample_streak >= 2) h->sample_skip = h->opt.sample_reuse;
+            const bool worth = kept < (use_tc ? 0.60 : 0.90);
+            if (!worth) {
+                if (sampling) {
+                    rc = list_all(2, kSample);
+                    if (sig != h->sample_sig) h->sample_streak = 0;
+                    if (++h->sample_streak >= 2) h->sample_skip = h->opt.sample_reuse;
+                }
             } else {
-                rc = bounds_pass(2, kSample);
                 h->sample_streak = 0;
                 pruned = kept < 0.5;
+                if (use_tc) {
+                    // Two passes (scht_select.cuh): first every tile scans the super-groups nearest to its queries, which gives
+                    // every query -- also one whose approximate leaf lies in the wrong cluster -- a tight bound; then the bound
+                    // test selects the pages of the main scan for all tiles.
+                    CU_TRY(cudaMemsetAsync(ctr + 5, 0, 8, s));
+                    rc = bounds_pass(0, 1, 1);
+                    if (rc) return rc;
+                    rc = launch_tc_scan(kWriteState, false);
+                    if (rc) return rc;
+                    CU_TRY(cudaMemsetAsync(ctr + 5, 0, 8, s));
+                    rc = bounds_pass(0, 1, 0);
+                } else if (sampling) {
+                    rc = bounds_pass(2, kSample, 0);
+                }
             }
             h->sample_sig = sig;
-            launches++;
-        } else {
-            rc = bounds_pass(0, 1);
-            launches++;
-            pruned = true;  // unknown: assume short lists (small batches)
         }
         if (rc) return rc;
     }
@@ -386,71 +467,16 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
     P.mode = (brute && !use_tc) ? kScanAll : kScanList;
     P.write_mode = keys_wanted ? kWriteKeys : kWriteFinal;
     if (use_tc) {
-        TcScanParams TC{};
-        TC.S = P;
-        TC.I = I;
-        TC.brute = brute ? 1 : 0;
-        TC.n_stages = tc_stages;
-        // Tail effect: n_tiles CTAs of equal length on n_sm SMs take ceil(n_tiles/n_sm) rounds (782 tiles on 148 SMs: 6 rounds
-        // for 5.28 rounds of work).  Splitting every tile's page list into S segments (own CTA each, partial lists merged by
-        // k_merge_partial) makes the rounds S times shorter: pick the S <= 8 with the smallest ceil(S*n_tiles/n_sm)/S, charging
-        // 5 % per extra segment for the repeated set-up and the looser early bounds (measured).  Also what keeps a SMALL batch from
-        // running on a handful of SMs.  Not with pruned page lists: their pages are not spread over the page index range.
-        int n_seg = 1;
-        if (!keys_wanted && h->opt.tc_split && !(pruned && h->opt.tc_split == 1 && n_tiles_main >= h->n_sm)) {
-            double best = 1e30;
-            for (int S = 1; S <= 8; S++) {
-                if (S > 1 && (page_hi - page_lo) / S < 64) break;
-                const double rounds = std::ceil((double)S * n_tiles_main / h->n_sm) / S * (1.0 + 0.05 * (S - 1));
-                if (rounds < best - 1e-9) {
-                    best = rounds;
-                    n_seg = S;
-                }
-            }
-            if (h->opt.tc_split > 1) n_seg = std::min(8, h->opt.tc_split);  // forced
-            if (n_seg > 1) {
-                CU_TRY(h->seg_keys.reserve((size_t)n_seg * nq * K * sizeof(uint64_t)));
-                TC.S.keys_out = h->seg_keys.as<uint64_t>();
-                TC.S.n_slices = 0;
-                TC.n_seg = n_seg;
-                TC.seg_page0 = page_lo;
-                TC.seg_pages = (page_hi - page_lo + n_seg - 1) / n_seg;
-            }
-        }
-        if (n_seg == 1) TC.n_seg = 1;
-        size_t smem = tc_smem_bytes(T.dpad, I.kp, K, tc_stages);
-        // One K slice per page (narrow points): two issuers, one per page parity, each issuing the page's two N=128 half-page
-        // chains (+3 % over four issuers; whole-page N=256 chains cost 2.4 % there).  Several slices per page (wide points): the
-        // MMA time counts, and one N=256 chain per page (128 instead of 2 x 92 cycles per K16 step) beats four issuers of
-        // half-page chains by 2 % (D=128) to 5 % (D=32).
-        const bool wide = I.kp > kTcKSlice;
-        bool want_n256 = (h->opt.tc_n256 < 0) ? wide : (h->opt.tc_n256 != 0);
-        int n_iss = (wide && !want_n256) ? 4 : 2;
-        if (h->opt.tc_issuers == 2 || h->opt.tc_issuers == 4) n_iss = h->opt.tc_issuers;
-        auto launch_tc = [&](auto kernel, int threads) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) kernel<<<n_tiles_main * n_seg, threads, smem, s>>>(TC);
-            return e;
-        };
-        const bool rows = T.rows != nullptr;  // wide points: exact re-evaluation from the row-major copy
-        const bool n256 = n_iss == 2 && want_n256;
-        if (n256) CU_TRY(rows ? launch_tc(k_scan_tc<2, true, true>, tc_threads(2)) : launch_tc(k_scan_tc<2, false, true>, tc_threads(2)));
-        else if (n_iss == 2) CU_TRY(rows ? launch_tc(k_scan_tc<2, true, false>, tc_threads(2)) : launch_tc(k_scan_tc<2, false, false>, tc_threads(2)));
-        else CU_TRY(rows ? launch_tc(k_scan_tc<4, true, false>, tc_threads(4)) : launch_tc(k_scan_tc<4, false, false>, tc_threads(4)));
-        CU_TRY(cudaGetLastError());
-        if (n_seg > 1) {
-            k_merge_partial<<<(nq + 127) / 128, 128, 0, s>>>(T, h->seg_keys.as<uint64_t>(), n_seg, nq, K, brute ? 1 : 0, P.idx_out, P.d2_out, P.dist_out);
-            CU_TRY(cudaGetLastError());
-            launches++;
-        }
+        int rc = launch_tc_scan(P.write_mode, true);
+        if (rc) return rc;
         h->tc_batches++;
         used_tc = true;
     } else {
         int rc = launch_scan(h, variant, P, s);
         if (rc) return rc;
+        launches++;
+        scans++;
     }
-    launches++;
-    scans++;
     if (timed) CU_TRY(cudaEventRecord(h->ev[4], s));
     if (st) {
         unsigned long long c[16];
@@ -966,13 +992,14 @@ extern "C" int scht_handle_info(const scht_handle* h, int32_t* dim, int64_t* n_p
     return SCHT_OK;
 }
 
-extern "C" int scht_handle_layout(const scht_handle* h, int32_t* n_devices, int32_t* mode, int32_t* n_scan_groups, int64_t* n_scan_pages,
-                                  int32_t* leaf_begin, int32_t* leaf_end) {
+extern "C" int scht_handle_layout(const scht_handle* h, int32_t* n_devices, int32_t* mode, int32_t* n_scan_groups, int32_t* n_super_groups,
+                                  int64_t* n_scan_pages, int32_t* leaf_begin, int32_t* leaf_end) {
     if (!h) return scht::fail(SCHT_ERR_INVALID_ARG, "handle is NULL");
     const scht_handle* x = h->subs.empty() ? h : h->subs[0];
     if (n_devices) *n_devices = h->subs.empty() ? 1 : (int)h->subs.size();
     if (mode) *mode = h->multi_mode;
     if (n_scan_groups) *n_scan_groups = x->I.kp ? x->I.n_groups : 0;
+    if (n_super_groups) *n_super_groups = x->I.kp ? x->I.n_supers : 0;
     if (n_scan_pages) *n_scan_pages = x->I.kp ? x->I.n_spages : 0;
     if (leaf_begin) *leaf_begin = x->leaf_lo;
     if (leaf_end) *leaf_end = x->leaf_hi;

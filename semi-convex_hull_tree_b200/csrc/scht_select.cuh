@@ -9,10 +9,16 @@
 // comparisons carry the rounding slack ball_eps(dim), so a page holding a true neighbour is never skipped; which pages
 // are scanned never changes a result bit (DESIGN.md "Result contract").
 //
-// One CTA per 128-query tile (thread = query).  Level 1: every group ball against every query; level 2: the pages of
-// the groups that survive for at least one query, tested by the queries that need the group.  Output: ascending page
-// ranges per tile in the layout PageWalk reads ([kMaxCuts][kJobRanges] flat = kRangeCap ranges); overflow widens the
-// last range (scans more, stays exact).
+// One CTA per 128-query tile (thread = query).  Level 1: every super-group ball against every query; level 2: the pages
+// of the super-groups that survive for at least one query, tested by the queries that need the super-group.  Output:
+// ascending page ranges per tile in the layout PageWalk reads ([kMaxCuts][kJobRanges] flat = kRangeCap ranges); overflow
+// widens the last range (scans more, stays exact).
+//
+// mode kSelNearest (first pass of a pruned batch): only level 1, and instead of testing bounds every query names the
+// super-group whose centre is nearest; the tile scans those super-groups first.  A query whose approximate leaf lies in
+// the "wrong" cluster has a seed bound several times too large, and one such query would make the whole tile list a
+// large part of the image; after this pass its list holds real neighbours and the bound test of the second pass is tight
+// for every query.
 #pragma once
 #include "scht_kernels.cuh"
 
@@ -29,6 +35,7 @@ struct SelectParams {
     int2* ranges;             // [n_tiles][kRangeCap]
     int* n_ranges;            // [n_tiles][kMaxCuts]
     int sel_mode, sel_step;   // tile subset (tile_of_selection)
+    int nearest;              // 1: kSelNearest pass (see above)
     unsigned long long* counters;  // [4] ball tests (per query), [5] pages listed x queries
 };
 
@@ -138,43 +145,77 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
             out[n_out++] = make_int2(cur_b, cur_e);
         }
     };
-    auto add_page = [&](int pg) {  // pages arrive in ascending order (a boundary page may repeat)
+    auto add_pages = [&](int pb, int pe) {  // page runs arrive in ascending order (a boundary page may repeat)
         if (cur_b < 0) {
-            cur_b = pg;
-            cur_e = pg + 1;
-        } else if (pg <= cur_e) {
-            cur_e = max(cur_e, pg + 1);
+            cur_b = pb;
+            cur_e = pe;
+        } else if (pb <= cur_e) {
+            cur_e = max(cur_e, pe);
         } else {
             flush();
-            cur_b = pg;
-            cur_e = pg + 1;
+            cur_b = pb;
+            cur_e = pe;
         }
     };
 
-    for (int g0 = 0; g0 < I.n_groups; g0 += kSelGroups) {
-        const int ng = min(kSelGroups, I.n_groups - g0);
+    if (P.nearest) {
+        // ---- first pass: the super-group nearest to each query ----
+        int* best_s = reinterpret_cast<int*>(cs);  // reused after the loop: [kSelQ] (cs holds >= kSelGroups * 16 floats >= 128 ints when DS >= 8)
+        float bd = 3.4e38f;
+        int bi = -1;
+        for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
+            const int ng = min(kSelGroups, I.n_supers - g0);
+            __syncthreads();
+            stage(I.scen, I.srad, g0, ng);
+            __syncthreads();
+            if (valid)
+                for (int gi = 0; gi < ng; gi++) {
+                    const float d = dist2(cs + (size_t)gi * DS);
+                    if (d < bd) bd = d, bi = g0 + gi;
+                }
+        }
+        tests += valid ? (unsigned long long)I.n_supers : 0ull;
+        __syncthreads();
+        best_s[t] = bi;
+        __syncthreads();
+        if (t == 0) {
+            // ascending, unique (insertion sort of <= 128 small integers, once per tile)
+            int m = 0;
+            for (int i = 0; i < nq_tile; i++) {
+                const int v = best_s[i];
+                if (v < 0) continue;
+                int j = m;
+                while (j > 0 && best_s[j - 1] > v) j--;
+                if (j > 0 && best_s[j - 1] == v) continue;
+                for (int k = m; k > j; k--) best_s[k] = best_s[k - 1];
+                best_s[j] = v;
+                m++;
+            }
+            for (int i = 0; i < m; i++) add_pages(I.spage[best_s[i]], I.spage[best_s[i] + 1]);
+        }
+    } else
+    for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
+        const int ng = min(kSelGroups, I.n_supers - g0);
         __syncthreads();  // previous round's readers of cs are done
-        stage(I.gcen, I.grad, g0, ng);
+        stage(I.scen, I.srad, g0, ng);
         __syncthreads();
         unsigned int gm = 0;
         if (valid)
             for (int gi = 0; gi < ng; gi++)
                 if (needs(cs + (size_t)gi * DS, rs[gi])) gm |= 1u << gi;
-        tests += (unsigned long long)ng;
+        tests += valid ? (unsigned long long)ng : 0ull;
         const unsigned int wm = __reduce_or_sync(0xffffffffu, gm);
         if (lane == 0 && wm) atomicOr(&s_mask, wm);
         __syncthreads();
         unsigned int tile_mask = s_mask;
         __syncthreads();
         if (t == 0) s_mask = 0u;
-        while (tile_mask) {  // block-uniform: the groups some query of the tile needs
+        while (tile_mask) {  // block-uniform: the super-groups some query of the tile needs
             const int gi = __ffs(tile_mask) - 1;
             tile_mask &= tile_mask - 1;
             const int g = g0 + gi;
-            const int sb = I.gslot[g], se = I.gslot[g + 1];
-            if (se <= sb) continue;
+            const int pb = I.spage[g], pe = I.spage[g + 1];
             const bool mine = (gm >> gi) & 1u;
-            const int pb = sb >> 8, pe = (se + kPage - 1) >> 8;
             for (int p0 = pb; p0 < pe; p0 += kSelPages) {
                 const int np = min(kSelPages, pe - p0);
                 __syncthreads();  // cs free; s_mask reset visible
@@ -194,7 +235,7 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
                     while (m) {
                         const int pi = __ffs(m) - 1;
                         m &= m - 1;
-                        add_page(p0 + pi);
+                        add_pages(p0 + pi, p0 + pi + 1);
                     }
                 }
             }

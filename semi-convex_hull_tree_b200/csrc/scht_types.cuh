@@ -60,20 +60,25 @@ struct DevTree {
     const int* cut_path;      // [n_cuts][cut_depth+1] root-side path of each cut node (node ids, -1 padded), cut node last
 };
 
-// The SCAN-ORDER image used by the tensor-core prefilter scan: the resident points re-ordered into spatially tight
-// "scan groups" (two Lloyd iterations over strided seeds, scht_create.cu), 256 consecutive slots = one scan page.
-// Every scan page and every group carries a bounding ball (centre, radius), so a query can skip a page whose ball
-// lies beyond its current K-th distance (k_select_pages).  slot_pos maps a slot back to the sorted position the
-// result contract is written in (key = d2 | r | pos).
+// The SCAN-ORDER image used by the tensor-core prefilter scan: the resident points re-ordered so that 256 consecutive
+// slots (one scan page) are spatially tight.  Built in scht_create.cu: fine k-means groups (~512 points, two Lloyd
+// iterations over strided seeds), the groups ordered by a recursive bisection of their centroids (neighbours in the order
+// are neighbours in space), and a page break (padding slots) wherever two consecutive groups are separated by empty
+// space, so that no page straddles two clusters.  Runs of <= kSuperPages pages between breaks form SUPER-GROUPS.  Every
+// super-group and every page carries a bounding ball (centre, radius): a query skips a ball that lies beyond its current
+// K-th distance (k_select_pages).  slot_pos maps a slot back to the sorted position the result contract is written in
+// (key = d2 | r | pos); padding slots hold -1.
+constexpr int kSuperPages = 32;
 struct ScanImage {
     const unsigned char* tcpages;  // per scan page: FP16 image [kp/8][32][8][8] (kp*512 B): s p'_j, then norm hi/mid/lo
-    const int* slot_pos;           // [n_spages*256] sorted position of a slot, -1 on padding (last page only)
+    const int* slot_pos;           // [n_spages*256] sorted position of a slot, -1 on padding
+    const int* pcnt;               // [n_spages] real points of the page
     const float* pcen;             // [n_spages][dpad] centre of the page's points
     const float* prad;             // [n_spages] radius (upper bound) around pcen
-    const float* gcen;             // [n_groups][dpad]
-    const float* grad;             // [n_groups]
-    const int* gslot;              // [n_groups+1] first slot of each group (groups are contiguous slot ranges)
-    int n_slots, n_spages, n_groups;
+    const float* scen;             // [n_supers][dpad]
+    const float* srad;             // [n_supers]
+    const int* spage;              // [n_supers+1] first page of each super-group
+    int n_slots, n_spages, n_supers, n_groups;  // n_slots = n_spages*256 (padding included); n_groups: k-means groups the order was built from
     const float* mean;             // [dpad] centre the image is taken around
     const float* pmax;             // [dpad] max |p_j - mean_j|
     float pnorm_max;               // max |p - mean|_2

@@ -127,13 +127,13 @@ def test_page_selection_prunes_clustered_data(pkg, orc, dim, K):
     oi, od2, _, _, _ = orc.knn(ht, q[:1500], K, alg=2)
     ix = pkg.Index(ht, options={"tc": 1})
     lay = ix.layout()
-    assert lay["scan_groups"] > 1 and lay["scan_pages"] == (n + 255) // 256
+    assert lay["scan_groups"] > 1 and lay["super_groups"] >= 200 and (n + 255) // 256 <= lay["scan_pages"] <= 1.1 * n / 256
     idx, d2, st = ix.query(q, K, want_stats=True)
     assert_bit_equal(idx[:1500], oi, "idx")
     assert_bit_equal(d2[:1500], od2, "dist2")
     assert st["prefilter_batches"] == 1
     frac = st["pages_listed"] / (nq * lay["scan_pages"])
-    assert frac < 0.2, "ball test kept %.3f of the scan pages on well separated clusters" % frac
+    assert frac < 0.06, "ball test kept %.3f of the scan pages on well separated clusters" % frac
     for opts in ({"page_select": 0}, {"traverse_sampling": 0}, {"tc_split": 4}, {"tc": 0}):
         for k, v in opts.items():
             ix.set_option(k, v)
