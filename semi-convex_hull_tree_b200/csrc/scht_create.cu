@@ -829,6 +829,7 @@ int create_handle(const scht_tree_desc* t, int device, int leaf_begin, int leaf_
         CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CU_TRY(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
         for (auto& e : h->ev) CU_TRY(cudaEventCreate(&e));
+        for (auto& e : h->ev_fp) CU_TRY(cudaEventCreate(&e));
         for (int i = 0; i < 2; i++) {
             CU_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
             CU_TRY(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));

@@ -101,13 +101,13 @@ int launch_traverse(scht_handle* h, const TraverseParams& P, cudaStream_t s) {
 
 // page selection by bounding balls (scht_select.cuh); the query lives in registers up to 64 dimensions
 int select_regs(int dpad) { return dpad <= 16 ? 16 : dpad <= 32 ? 32 : dpad <= 64 ? 64 : 0; }
-bool select_fits(const scht_handle* h) { return (int)select_smem_bytes(select_regs(h->T.dpad), h->T.dpad) <= h->max_smem; }
+bool select_fits(const scht_handle* h) { return (int)select_smem_bytes(select_regs(h->T.dpad), h->T.dpad, h->I.n_supers) <= h->max_smem; }
 int launch_select(scht_handle* h, const SelectParams& P, cudaStream_t s) {
     const int n_tiles = (P.nq + kSelQ - 1) / kSelQ;
     const int blocks = selection_size(n_tiles, P.sel_mode, P.sel_step);
     if (blocks == 0) return SCHT_OK;
     const int dp = select_regs(P.T.dpad);
-    const size_t smem = select_smem_bytes(dp, P.T.dpad);
+    const size_t smem = select_smem_bytes(dp, P.T.dpad, P.I.n_supers);
     auto go = [&](auto kernel) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) kernel<<<blocks, kSelQ, smem, s>>>(P);
@@ -285,6 +285,7 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
     const int page_hi = use_tc ? I.n_spages : (P.pos_hi + kPage - 1) / kPage;
     const int n_list_pages = std::max(1, page_hi - page_lo);
     bool pruned = false;  // the page lists are (much) shorter than "every page"
+    bool first_pass = false;
 
     // ---- the prefilter scan kernel over the current page lists (used for the first pass of a pruned batch and for the main scan)
     auto launch_tc_scan = [&](int write_mode, bool allow_split) -> int {
@@ -331,6 +332,12 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
         bool want_n256 = (h->opt.tc_n256 < 0) ? wide : (h->opt.tc_n256 != 0);
         int n_iss = (wide && !want_n256) ? 4 : 2;
         if (h->opt.tc_issuers == 2 || h->opt.tc_issuers == 4) n_iss = h->opt.tc_issuers;
+        // a page with at least as many K slices as stages: one issuer takes every page (TcScanParams::single_issuer)
+        const int n_slices = (I.kp + kTcKSlice - 1) / kTcKSlice;
+        if (n_slices >= tc_stages) {
+            n_iss = 2;
+            TC.single_issuer = 1;
+        }
         auto launch_tc = [&](auto kernel, int threads) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) kernel<<<n_tiles_main * n_seg, threads, smem, s>>>(TC);
@@ -424,16 +431,20 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             rc = list_all(0, 1);
         } else {
             // probe: the sampled tiles (or all tiles of a small batch)
-            unsigned long long listed = 0;
+            unsigned long long probe[3] = {0, 0, 0};  // [0] pages listed x queries (tile unions), [2] (query, page) pairs within the bound
             rc = bounds_pass(sampling ? 1 : 0, kSample, 0);
             if (rc) return rc;
-            CU_TRY(cudaMemcpyAsync(&listed, ctr + 5, 8, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaMemcpyAsync(probe, ctr + 5, 24, cudaMemcpyDeviceToHost, s));
             CU_TRY(cudaStreamSynchronize(s));
             long long probed_q = 0;
             for (int t = 0; t < n_tiles_main; t += kSample) probed_q += std::min(tq_main, nq - t * tq_main);
-            const double kept = (double)listed / std::max(1.0, (double)probed_q * n_list_pages);
-            // a prefilter page costs ~1/10 of an exact page, so pruning must remove much more before it pays for itself
-            const bool worth = kept < (use_tc ? 0.60 : 0.90);
+            const double denom = std::max(1.0, (double)probed_q * n_list_pages);
+            const double kept = (double)probe[0] / denom;      // what the tiles would scan with the bounds they have now
+            const double kept_q = (double)probe[2] / denom;    // what the queries need, one by one
+            // a prefilter page costs ~1/10 of an exact page, so pruning must remove much more before it pays for itself.  Prefilter
+            // scan: the decision looks at the per-query need -- a few queries with a loose seed bound inflate their tiles' unions,
+            // which is exactly what the first pass below repairs.
+            const bool worth = use_tc ? (kept < 0.60 || kept_q < 0.15) : kept < 0.90;
             if (!worth) {
                 if (sampling) {
                     rc = list_all(2, kSample);
@@ -442,7 +453,7 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
                 }
             } else {
                 h->sample_streak = 0;
-                pruned = kept < 0.5;
+                pruned = use_tc || kept < 0.5;
                 if (use_tc) {
                     // Two passes (scht_select.cuh): first every tile scans the super-groups nearest to its queries, which gives
                     // every query -- also one whose approximate leaf lies in the wrong cluster -- a tight bound; then the bound
@@ -450,8 +461,11 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
                     CU_TRY(cudaMemsetAsync(ctr + 5, 0, 8, s));
                     rc = bounds_pass(0, 1, 1);
                     if (rc) return rc;
+                    if (timed) CU_TRY(cudaEventRecord(h->ev_fp[0], s));
                     rc = launch_tc_scan(kWriteState, false);
                     if (rc) return rc;
+                    if (timed) CU_TRY(cudaEventRecord(h->ev_fp[1], s));
+                    first_pass = true;
                     CU_TRY(cudaMemsetAsync(ctr + 5, 0, 8, s));
                     rc = bounds_pass(0, 1, 0);
                 } else if (sampling) {
@@ -504,7 +518,14 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             st->ms_seed_scan += b;
             st->ms_main_scan += c2;
             st->ms_traverse += tr;
+            if (first_pass) {
+                float fp = 0;
+                CU_TRY(cudaEventElapsedTime(&fp, h->ev_fp[0], h->ev_fp[1]));
+                st->ms_first_pass += fp;
+                st->ms_traverse -= fp;
+            }
         }
+        st->first_pass_batches += first_pass ? 1 : 0;
     }
     return SCHT_OK;
 }
@@ -721,6 +742,8 @@ extern "C" void scht_destroy(scht_handle* h) {
         b->release();
     for (PinBuf* b : {&h->pin_q[0], &h->pin_q[1], &h->pin_out[0], &h->pin_out[1]}) b->release();
     for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : h->ev_fp)
         if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);

@@ -91,6 +91,7 @@ struct scht_handle {
     cudaStream_t copy_stream = nullptr;  // H2D of the next batch (scht_query pipeline)
     cudaStream_t out_stream = nullptr;   // D2H of the previous batch
     cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_fp[2] = {};  // first pass of a pruned batch (k_scan_tc over the nearest super-groups)
     cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {};  // per pipeline slot: queries uploaded, kernels done, results downloaded
     scht::DevTree T{};
     scht::ScanImage I{};

@@ -36,17 +36,18 @@ struct SelectParams {
     int* n_ranges;            // [n_tiles][kMaxCuts]
     int sel_mode, sel_step;   // tile subset (tile_of_selection)
     int nearest;              // 1: kSelNearest pass (see above)
-    unsigned long long* counters;  // [4] ball tests (per query), [5] pages listed x queries
+    unsigned long long* counters;  // [4] ball tests (per query), [5] pages listed x queries, [7] (query, page) pairs that pass the bound test
 };
 
 constexpr int kSelQ = 128;    // queries per tile (= kTcQ)
 constexpr int kSelGroups = 16;  // group balls staged per round
 constexpr int kSelPages = 8;    // page balls staged per round
 
-__host__ __device__ inline size_t select_smem_bytes(int dp_regs, int dpad) {
+__host__ __device__ inline size_t select_smem_bytes(int dp_regs, int dpad, int n_supers) {
     const int ds = dp_regs > 0 ? dp_regs : dpad;
     size_t b = (size_t)kSelGroups * ds * 4 + kSelGroups * 4;
     if (dp_regs == 0) b += (size_t)dpad * kSelQ * 4;
+    b += (size_t)((n_supers + 31) / 32) * 4;  // bitmap of the nearest pass
     return b + 16;
 }
 
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
     float* cs = reinterpret_cast<float*>(sel_smem);       // [kSelGroups][DS] staged centres
     float* rs = cs + (size_t)kSelGroups * DS;             // [kSelGroups] staged radii
     float* qs = rs + kSelGroups;                          // DP == 0: [dpad][kSelQ]
+    unsigned int* near_map = reinterpret_cast<unsigned int*>(qs + (DP > 0 ? 0 : (size_t)dpad * kSelQ));  // [(n_supers+31)/32] bits (nearest pass)
     const int t = threadIdx.x, lane = t & 31;
     const int n_tiles = (P.nq + kSelQ - 1) / kSelQ;
     const int tile = tile_of_selection((int)blockIdx.x, P.sel_mode, P.sel_step);
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
 
     int2* out = P.ranges + (size_t)tile * kRangeCap;
     int n_out = 0, cur_b = -1, cur_e = -1;  // thread 0 only
-    unsigned long long listed = 0, tests = 0;
+    unsigned long long listed = 0, tests = 0, need_pairs = 0;
     auto flush = [&]() {
         if (n_out == kRangeCap) {
             listed += (unsigned long long)(cur_e - out[n_out - 1].y);
@@ -160,7 +162,8 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
 
     if (P.nearest) {
         // ---- first pass: the super-group nearest to each query ----
-        int* best_s = reinterpret_cast<int*>(cs);  // reused after the loop: [kSelQ] (cs holds >= kSelGroups * 16 floats >= 128 ints when DS >= 8)
+        const int n_words = (I.n_supers + 31) / 32;
+        for (int w = t; w < n_words; w += kSelQ) near_map[w] = 0u;
         float bd = 3.4e38f;
         int bi = -1;
         for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
@@ -175,24 +178,17 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
                 }
         }
         tests += valid ? (unsigned long long)I.n_supers : 0ull;
+        if (bi >= 0) atomicOr(&near_map[bi >> 5], 1u << (bi & 31));
         __syncthreads();
-        best_s[t] = bi;
-        __syncthreads();
-        if (t == 0) {
-            // ascending, unique (insertion sort of <= 128 small integers, once per tile)
-            int m = 0;
-            for (int i = 0; i < nq_tile; i++) {
-                const int v = best_s[i];
-                if (v < 0) continue;
-                int j = m;
-                while (j > 0 && best_s[j - 1] > v) j--;
-                if (j > 0 && best_s[j - 1] == v) continue;
-                for (int k = m; k > j; k--) best_s[k] = best_s[k - 1];
-                best_s[j] = v;
-                m++;
+        if (t == 0)  // the marked super-groups in ascending order
+            for (int w = 0; w < n_words; w++) {
+                unsigned int m = near_map[w];
+                while (m) {
+                    const int sgi = 32 * w + __ffs(m) - 1;
+                    m &= m - 1;
+                    add_pages(I.spage[sgi], I.spage[sgi + 1]);
+                }
             }
-            for (int i = 0; i < m; i++) add_pages(I.spage[best_s[i]], I.spage[best_s[i] + 1]);
-        }
     } else
     for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
         const int ng = min(kSelGroups, I.n_supers - g0);
@@ -226,6 +222,7 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
                     for (int pi = 0; pi < np; pi++)
                         if (needs(cs + (size_t)pi * DS, rs[pi])) pm |= 1u << pi;
                 if (mine) tests += (unsigned long long)np;
+                need_pairs += (unsigned long long)__popc(pm);
                 const unsigned int wpm = __reduce_or_sync(0xffffffffu, pm);
                 if (lane == 0 && wpm) atomicOr(&s_mask, wpm);
                 __syncthreads();
@@ -249,8 +246,14 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
     const int total = s_nout;
     if (t < kMaxCuts) P.n_ranges[(size_t)tile * kMaxCuts + t] = max(0, min(kJobRanges, total - t * kJobRanges));
     if (P.counters) {
-        for (int o = 16; o; o >>= 1) tests += __shfl_xor_sync(0xffffffffu, tests, o);
-        if (lane == 0) atomicAdd(&P.counters[4], tests);
+        for (int o = 16; o; o >>= 1) {
+            tests += __shfl_xor_sync(0xffffffffu, tests, o);
+            need_pairs += __shfl_xor_sync(0xffffffffu, need_pairs, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&P.counters[4], tests);
+            if (need_pairs) atomicAdd(&P.counters[7], need_pairs);
+        }
         if (t == 0) atomicAdd(&P.counters[5], listed * (unsigned long long)nq_tile);
     }
 }

@@ -50,6 +50,9 @@ struct TcScanParams {
     ScanParams S;            // q, q_order, q_leaf, nq, K, write_mode, pos range, ranges (tile = 128 queries), state, outputs
     ScanImage I;             // the scan-order image: FP16 pages, slot -> position, centre / scale of the operands
     int brute;               // 1: keys carry the ORIGINAL index and no approximate-leaf bit (scht_brute_force)
+    int single_issuer;       // 1: MMA issuer 0 issues every page (set when a page has at least as many K slices as there are stages: an
+                             //    issuer that skips the other parity's pages would run a whole ring round ahead of the producer, and a
+                             //    parity wait cannot tell round r from round r+2)
     int n_stages;            // slice stages in shared memory (3..kTcMaxStages)
     int n_seg;               // page segments per tile (>= 1): CTA b scans segment b / n_tiles of tile b % n_tiles and, when
     int seg_pages;           //   n_seg > 1, writes its key lists to S.keys_out[segment][query][K] (merged by k_merge_partial);
@@ -312,6 +315,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
         // n_iss == 2: warp 17+b issues both half pages of the pages with parity b (3 % faster on one-slice pages);
         // n_iss == 4: warp 17+m issues half page m&1 of the pages with parity m>>1 (7 % faster when a page has several K slices)
         const int m_iss = warp - (kTcEpiWarps + 1);
+        const bool single = (N_ISS == 2) && TP.single_issuer;  // issuer 0 takes every page, issuer 1 idles
         const int my_par = (N_ISS == 2) ? m_iss : (m_iss >> 1);
         const int h_lo = (N_ISS == 2) ? 0 : (m_iss & 1), h_hi = (N_ISS == 2) ? 1 : (m_iss & 1);
         constexpr int kHalf = kPage / 2;  // N of one MMA: a half page
@@ -324,10 +328,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
         const uint32_t kBStage = stage_bytes / 16;
         const uint64_t da0 = umma_desc_kmajor(smem_u32(sA), (kTcQ / 8) * 128, 128);
         const uint64_t db0 = umma_desc_kmajor(smem_u32(stage_mem), (kPage / 8) * 128, 128);
-        const uint32_t d_tmem = tmem + (uint32_t)my_par * kPage;  // buffers 2*par (half 0) and 2*par+1 (half 1)
-        uint64_t* const tfull_p = &tfull_b[2 * my_par];
-        uint64_t* const tempty_p = &tempty_b[2 * my_par];
-        uint32_t st = 0, ph = 0, pg = 0, use_ph = 1;  // use_ph: parity to wait for on tempty (the first use passes immediately)
+        uint32_t st = 0, ph = 0, pg = 0;
         auto advance = [&](uint32_t k) {
             st += k;
             while (st >= (uint32_t)n_stages) {
@@ -335,12 +336,19 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                 ph ^= 1;
             }
         };
+        if (single && m_iss != 0) run_hi = 0;  // (falls through to the teardown)
+        else
         while (walk.next_range(run_lo, run_hi)) for (page = run_lo; page < run_hi; page++) {
-            if ((int)(pg & 1) != my_par) {  // the other parity's issuer handles this page
+            const int par = single ? (int)(pg & 1) : my_par;
+            if ((int)(pg & 1) != par) {  // the other parity's issuer handles this page
                 advance((uint32_t)n_slices);
                 pg++;
                 continue;
             }
+            const uint32_t d_tmem = tmem + (uint32_t)par * kPage;  // buffers 2*par (half 0) and 2*par+1 (half 1)
+            uint64_t* const tfull_p = &tfull_b[2 * par];
+            uint64_t* const tempty_p = &tempty_b[2 * par];
+            const uint32_t use_ph = ((pg >> 1) & 1) ^ 1;  // parity to wait for on tempty: the buffer pair's (pg/2)-th use (the first passes immediately)
             for (int s = 0; s < n_slices; s++) {
                 mbar_wait(&full_b[st], ph);
                 TC_STAMP(s == 0, pg, 3);
@@ -384,7 +392,6 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                 }
                 advance(1);
             }
-            use_ph ^= 1;
             TC_STAMP(true, pg, 4);
             pg++;
         }
