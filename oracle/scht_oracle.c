@@ -6,7 +6,7 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it; the
  * product (libscht_b200.so) never links, loads or calls anything in oracle/.
  *
- * PARITY PINNING: pinned against the reference itself — tests/test_oracle_vs_reference.py runs
+ * PARITY PINNING: pinned against the reference itself — tests/test_oracle_golden.py runs
  * oracle/_ref/ref_knn (the unmodified reference compiled from /root/reference, oracle/Makefile)
  * on the same inputs and requires bit-identical indices, dist2, dist, approximate leaves and
  * work counters; tests/golden/ holds committed fixtures produced by that binary

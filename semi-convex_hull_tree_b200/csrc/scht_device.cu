@@ -99,8 +99,8 @@ int launch_traverse(scht_handle* h, const TraverseParams& P, cudaStream_t s) {
     return SCHT_OK;
 }
 
-// page selection by bounding balls (scht_select.cuh); the query lives in registers up to 64 dimensions
-int select_regs(int dpad) { return dpad <= 16 ? 16 : dpad <= 32 ? 32 : dpad <= 64 ? 64 : 0; }
+// page selection by bounding balls (scht_select.cuh); the query lives in registers up to 128 dimensions
+int select_regs(int dpad) { return dpad <= 16 ? 16 : dpad <= 32 ? 32 : dpad <= 64 ? 64 : dpad <= 128 ? 128 : 0; }
 bool select_fits(const scht_handle* h) { return (int)select_smem_bytes(select_regs(h->T.dpad), h->T.dpad, h->I.n_supers) <= h->max_smem; }
 int launch_select(scht_handle* h, const SelectParams& P, cudaStream_t s) {
     const int n_tiles = (P.nq + kSelQ - 1) / kSelQ;
@@ -116,6 +116,7 @@ int launch_select(scht_handle* h, const SelectParams& P, cudaStream_t s) {
     if (dp == 16) CU_TRY(go(k_select_pages<16>));
     else if (dp == 32) CU_TRY(go(k_select_pages<32>));
     else if (dp == 64) CU_TRY(go(k_select_pages<64>));
+    else if (dp == 128) CU_TRY(go(k_select_pages<128>));
     else CU_TRY(go(k_select_pages<0>));
     CU_TRY(cudaGetLastError());
     return SCHT_OK;

@@ -14,8 +14,8 @@
 // ascending page ranges per tile in the layout PageWalk reads ([kMaxCuts][kJobRanges] flat = kRangeCap ranges); overflow
 // widens the last range (scans more, stays exact).
 //
-// mode kSelNearest (first pass of a pruned batch): only level 1, and instead of testing bounds every query names the
-// super-group whose centre is nearest; the tile scans those super-groups first.  A query whose approximate leaf lies in
+// mode kSelNearest (first pass of a pruned batch): no bound test; every query names the super-group whose centre is
+// nearest and, inside it, the two pages whose centres are nearest; the tile scans those pages first.  A query whose approximate leaf lies in
 // the "wrong" cluster has a seed bound several times too large, and one such query would make the whole tile list a
 // large part of the image; after this pass its list holds real neighbours and the bound test of the second pass is tight
 // for every query.
@@ -40,8 +40,9 @@ struct SelectParams {
 };
 
 constexpr int kSelQ = 128;    // queries per tile (= kTcQ)
-constexpr int kSelGroups = 16;  // group balls staged per round
+constexpr int kSelGroups = 32;  // super-group balls staged per round (one bit each in a 32-bit mask)
 constexpr int kSelPages = 8;    // page balls staged per round
+static_assert(kSuperPages <= 64, "k_select_pages marks the pages of one super-group in two 32-bit words");
 
 __host__ __device__ inline size_t select_smem_bytes(int dp_regs, int dpad, int n_supers) {
     const int ds = dp_regs > 0 ? dp_regs : dpad;
@@ -56,6 +57,7 @@ template <int DP>
 __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ unsigned int s_mask;
+    __shared__ unsigned int s_pm[2];  // first pass: page marks of one super-group (kSuperPages <= 64)
     __shared__ int s_nout;
     const DevTree& T = P.T;
     const ScanImage& I = P.I;
@@ -180,15 +182,47 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
         tests += valid ? (unsigned long long)I.n_supers : 0ull;
         if (bi >= 0) atomicOr(&near_map[bi >> 5], 1u << (bi & 31));
         __syncthreads();
-        if (t == 0)  // the marked super-groups in ascending order
-            for (int w = 0; w < n_words; w++) {
-                unsigned int m = near_map[w];
-                while (m) {
-                    const int sgi = 32 * w + __ffs(m) - 1;
-                    m &= m - 1;
-                    add_pages(I.spage[sgi], I.spage[sgi + 1]);
+        // the marked super-groups in ascending order; of each, the two pages nearest to every query that chose it
+        for (int w = 0; w < n_words; w++) {
+            unsigned int m = near_map[w];  // block-uniform
+            while (m) {
+                const int sgi = 32 * w + __ffs(m) - 1;
+                m &= m - 1;
+                const int pb = I.spage[sgi], pe = I.spage[sgi + 1];
+                const bool mine = bi == sgi;
+                float d1 = 3.4e38f, d2 = 3.4e38f;
+                int p1 = -1, p2 = -1;
+                for (int p0 = pb; p0 < pe; p0 += kSelPages) {
+                    const int np = min(kSelPages, pe - p0);
+                    __syncthreads();
+                    stage(I.pcen, I.prad, p0, np);
+                    if (t < 2) s_pm[t] = 0u;
+                    __syncthreads();
+                    if (mine)
+                        for (int pi = 0; pi < np; pi++) {
+                            const float d = dist2(cs + (size_t)pi * DS);
+                            if (d < d1) {
+                                d2 = d1, p2 = p1;
+                                d1 = d, p1 = p0 + pi;
+                            } else if (d < d2) {
+                                d2 = d, p2 = p0 + pi;
+                            }
+                        }
                 }
+                if (p1 >= 0) atomicOr(&s_pm[(p1 - pb) >> 5], 1u << ((p1 - pb) & 31));
+                if (p2 >= 0) atomicOr(&s_pm[(p2 - pb) >> 5], 1u << ((p2 - pb) & 31));
+                __syncthreads();
+                if (t == 0)
+                    for (int k = 0; k < 2; k++) {
+                        unsigned int pm = s_pm[k];
+                        while (pm) {
+                            const int pg = pb + 32 * k + __ffs(pm) - 1;
+                            pm &= pm - 1;
+                            add_pages(pg, pg + 1);
+                        }
+                    }
             }
+        }
     } else
     for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
         const int ng = min(kSelGroups, I.n_supers - g0);

@@ -14,7 +14,7 @@ constexpr int kStages = 4;
 constexpr int kQPerWarp = 8;       // queries owned by one consumer warp
 constexpr int kMaxLevel = 32;      // constraints beyond this depth are ignored by the pruning bound (still valid)
 #ifndef SCHT_SEED_POINTS
-#define SCHT_SEED_POINTS 512
+#define SCHT_SEED_POINTS 256
 #endif
 constexpr int kSeedPoints = SCHT_SEED_POINTS;  // size of the seed neighbourhood (positions) scanned before the traversal bounds are taken
 constexpr int kMaxCuts = 64;       // the traversal of one tile is split into <= 64 subtree jobs (one warp each)
@@ -68,7 +68,7 @@ struct DevTree {
 // super-group and every page carries a bounding ball (centre, radius): a query skips a ball that lies beyond its current
 // K-th distance (k_select_pages).  slot_pos maps a slot back to the sorted position the result contract is written in
 // (key = d2 | r | pos); padding slots hold -1.
-constexpr int kSuperPages = 32;
+constexpr int kSuperPages = 64;   // (the first-pass page marks of k_select_pages are two 32-bit words per super-group)
 struct ScanImage {
     const unsigned char* tcpages;  // per scan page: FP16 image [kp/8][32][8][8] (kp*512 B): s p'_j, then norm hi/mid/lo
     const int* slot_pos;           // [n_spages*256] sorted position of a slot, -1 on padding

@@ -4,7 +4,7 @@
 // constructor path of Convex_Tree<T> (reference: Code/Convex_Tree.h:518-548):
 //     build_tree (:708-857) -> build_simplified_tree (:685-705) -> sort_raw_data (:593-633)
 // and emits the flat SoA arrays of scht_tree_desc (include/scht.h).  Given the same data and seed the
-// arrays are bit-identical to what the reference's own tree holds (tests/test_builder_parity.py checks
+// arrays are bit-identical to what the reference's own tree holds (tests/test_oracle_golden.py checks
 // this against oracle/_ref when the reference is present, and against tests/golden/ always).
 //
 // This file must be compiled WITHOUT floating-point contraction (-ffp-contract=off) and without

@@ -171,7 +171,7 @@ def test_scan_group_counts(pkg, orc, monkeypatch, groups):
 def test_options_interface(pkg):
     rng = np.random.default_rng(1)
     ix = pkg.Index(pkg.HostTree(rng.random((5000, 6), dtype=np.float32), 0.01, seed=1))
-    assert ix.get_option("tc") == 2 and ix.get_option("seed_points") == 512
+    assert ix.get_option("tc") == 2 and ix.get_option("seed_points") == 256
     ix.set_option("tc", 0)
     ix.set_option("seed_points", 2048)
     assert ix.get_option("tc") == 0 and ix.get_option("seed_points") == 2048
