@@ -143,8 +143,6 @@ typedef struct scht_stats {
     double ms_seed_scan;         /* CUDA-event time of the seed scan (approximate leaves) */
     double ms_traverse;          /* CUDA-event time of the eligibility + page-selection / traversal kernels */
     double ms_main_scan;         /* CUDA-event time of the main scan (k_scan or k_scan_tc) */
-    double ms_first_pass;        /* CUDA-event time of the first prefilter pass of pruned batches (nearest super-groups; not in ms_traverse) */
-    int64_t first_pass_batches;  /* batches that ran the two-pass page selection */
 } scht_stats;
 
 /* Uploads the tree to `device` (CUDA ordinal) in the device layout described in DESIGN.md.

@@ -38,8 +38,7 @@ class Stats(C.Structure):
                 ("list_insertions", C.c_int64), ("hyperplane_tests", C.c_int64), ("descent_dists", C.c_int64),
                 ("batches", C.c_int64), ("ms_total", C.c_double), ("ms_device", C.c_double), ("ms_scan", C.c_double),
                 ("scan_launches", C.c_int64), ("kernel_launches", C.c_int64), ("pages_listed", C.c_int64),
-                ("prefilter_batches", C.c_int64), ("ms_seed_scan", C.c_double), ("ms_traverse", C.c_double), ("ms_main_scan", C.c_double),
-                ("ms_first_pass", C.c_double), ("first_pass_batches", C.c_int64)]
+                ("prefilter_batches", C.c_int64), ("ms_seed_scan", C.c_double), ("ms_traverse", C.c_double), ("ms_main_scan", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) k_page_balls(DevTree T, const int* __rest
 // bounding ball of a run of slots [first[b], first[b+1]) * unit (unit = 256: super-groups given by page boundaries)
 // centre: mean of the points of the run
 __global__ void __launch_bounds__(256) k_run_balls(DevTree T, const int* __restrict__ slot_pos, const int* __restrict__ first, int unit, float* __restrict__ cen,
-                                                   float* __restrict__ rad) {
+                                                   float* __restrict__ rad, int* __restrict__ count) {
     extern __shared__ float cen_s[];  // [dpad]
     __shared__ float red[8];
     const int g = blockIdx.x;
@@ -290,7 +290,10 @@ __global__ void __launch_bounds__(256) k_run_balls(DevTree T, const int* __restr
         m = fmaxf(m, d2);
     }
     m = block_max(m, red);
-    if (threadIdx.x == 0) rad[g] = sqrtf(m) * (1.f + ball_eps(T.dim)) + 1e-37f;
+    if (threadIdx.x == 0) {
+        rad[g] = sqrtf(m) * (1.f + ball_eps(T.dim)) + 1e-37f;
+        count[g] = (int)cnt;
+    }
 }
 
 // radius of every k-means group around its centroid (members = sorted keys [gslot[g], gslot[g+1]))
@@ -619,7 +622,7 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
     const int S = (int)spage_h.size() - 1;
 
     float *pcen = nullptr, *prad = nullptr, *scen = nullptr, *srad = nullptr;
-    int *pcnt = nullptr, *spage = nullptr;
+    int *pcnt = nullptr, *spage = nullptr, *scnt = nullptr;
     unsigned char* tcp = nullptr;
     TRY_T(dev_alloc(h, (size_t)n_spages * dpad, &pcen));
     TRY_T(dev_alloc(h, (size_t)n_spages, &prad));
@@ -627,11 +630,12 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
     TRY_T(dev_alloc(h, (size_t)S * dpad, &scen));
     TRY_T(dev_alloc(h, (size_t)S, &srad));
     TRY_T(dev_alloc(h, (size_t)S + 1, &spage));
+    TRY_T(dev_alloc(h, (size_t)S, &scnt));
     TRY_T(dev_alloc(h, (size_t)n_spages * tc_page_bytes(kp), &tcp));
     CU_T(cudaMemcpyAsync(spage, spage_h.data(), (size_t)(S + 1) * 4, cudaMemcpyHostToDevice, s));
     k_build_tcpages<<<(unsigned)(((size_t)n_spages * kPage + 255) / 256), 256, 0, s>>>(T, slot_pos, n_spages, d_mean, I.scale, I.norm_unit, kp, tcp);
     k_page_balls<<<n_spages, 256, dpad * sizeof(float), s>>>(T, slot_pos, pcen, prad, pcnt);
-    k_run_balls<<<S, 256, dpad * sizeof(float), s>>>(T, slot_pos, spage, kPage, scen, srad);
+    k_run_balls<<<S, 256, dpad * sizeof(float), s>>>(T, slot_pos, spage, kPage, scen, srad, scnt);
     CU_T(cudaGetLastError());
 
     // ---- bucket order of the leaves: by (ordered scan group nearest to the leaf's mean, leaf id), so that the queries of a
@@ -668,6 +672,7 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
     I.scen = scen;
     I.srad = srad;
     I.spage = spage;
+    I.scnt = scnt;
     I.n_slots = n_spages * kPage;
     I.n_spages = n_spages;
     I.n_supers = S;
@@ -829,7 +834,6 @@ int create_handle(const scht_tree_desc* t, int device, int leaf_begin, int leaf_
         CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CU_TRY(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
         for (auto& e : h->ev) CU_TRY(cudaEventCreate(&e));
-        for (auto& e : h->ev_fp) CU_TRY(cudaEventCreate(&e));
         for (int i = 0; i < 2; i++) {
             CU_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
             CU_TRY(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));

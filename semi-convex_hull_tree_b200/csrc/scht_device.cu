@@ -269,8 +269,14 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
     int tc_stages = kTcMaxStages;
     while (tc_stages > 3 && (int)tc_smem_bytes(T.dpad, I.kp, K, tc_stages) > h->max_smem) tc_stages--;
     if (I.kp > 0 && h->opt.tc_mode != 0 && (!brute || h->opt.brute_tc) && (int)tc_smem_bytes(T.dpad, I.kp, K, tc_stages) <= h->max_smem) {
+        const long long esig = ((long long)K << 1) | ((long long)kind << 9) | ((long long)(d_ext_bound ? 1 : 0) << 12) | ((long long)std::min(nq >> 10, 1 << 20) << 16);
         if (h->opt.tc_mode == 1) {
             use_tc = true;
+        } else if (h->elig_skip > 0 && esig == h->elig_sig) {
+            // the last batches of this shape all got the same verdict: no kernel, no host round trip (a wrong guess only costs
+            // time: queries the prefilter cannot handle pass everything to the exact path)
+            h->elig_skip--;
+            use_tc = h->elig_last != 0;
         } else {
             k_tc_eligibility<<<(nq + 127) / 128, 128, 0, s>>>(T, I, d_q, P.q_order, nq, K, P.state, d_ext_bound, ctr);
             launches++;
@@ -278,6 +284,10 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             CU_TRY(cudaMemcpyAsync(&ok, ctr + 6, 8, cudaMemcpyDeviceToHost, s));
             CU_TRY(cudaStreamSynchronize(s));
             use_tc = ok * 10 >= (unsigned long long)nq * 9;  // >= 90 % of the queries have a tight margin
+            if (esig != h->elig_sig || (int)use_tc != h->elig_last) h->elig_streak = 0;
+            if (++h->elig_streak >= 2) h->elig_skip = h->opt.sample_reuse;
+            h->elig_sig = esig;
+            h->elig_last = use_tc ? 1 : 0;
         }
     }
     const int tq_main = use_tc ? kTcQ : tq;
@@ -286,12 +296,13 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
     const int page_hi = use_tc ? I.n_spages : (P.pos_hi + kPage - 1) / kPage;
     const int n_list_pages = std::max(1, page_hi - page_lo);
     bool pruned = false;  // the page lists are (much) shorter than "every page"
-    bool first_pass = false;
+    const float* sel_bound = nullptr;  // per query: the bound k_select_pages tested with (prefilter scan with page selection)
 
     // ---- the prefilter scan kernel over the current page lists (used for the first pass of a pruned batch and for the main scan)
     auto launch_tc_scan = [&](int write_mode, bool allow_split) -> int {
         TcScanParams TC{};
         TC.S = P;
+        if (sel_bound) TC.S.ext_bound = sel_bound;
         TC.S.mode = kScanList;
         TC.S.write_mode = write_mode;
         TC.S.range_groups = kMaxCuts;
@@ -382,6 +393,14 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             SP.ranges = h->ranges.as<int2>();
             SP.n_ranges = h->n_ranges.as<int>();
             SP.counters = ctr;
+            SP.tighten = 1;
+            // the bound every query's test used goes to the scan kernel's filter: initialised with the external bound (or "none")
+            CU_TRY(h->sel_bound.reserve((size_t)nq * 4));
+            k_init_bounds<<<(nq + 255) / 256, 256, 0, s>>>(h->sel_bound.as<float>(), d_ext_bound, nq);
+            CU_TRY(cudaGetLastError());
+            launches++;
+            SP.bound_out = h->sel_bound.as<float>();
+            sel_bound = h->sel_bound.as<float>();
             P.range_groups = kMaxCuts;
         } else {
             TP.T = T;
@@ -400,12 +419,11 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             TP.counters = ctr;
             TP.ball_only = 0;
         }
-        auto bounds_pass = [&](int mode, int step, int nearest) -> int {
+        auto bounds_pass = [&](int mode, int step) -> int {
             launches++;
             if (use_tc) {
                 SP.sel_mode = mode;
                 SP.sel_step = step;
-                SP.nearest = nearest;
                 return launch_select(h, SP, s);
             }
             TP.sel_mode = mode;
@@ -432,20 +450,16 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             rc = list_all(0, 1);
         } else {
             // probe: the sampled tiles (or all tiles of a small batch)
-            unsigned long long probe[3] = {0, 0, 0};  // [0] pages listed x queries (tile unions), [2] (query, page) pairs within the bound
-            rc = bounds_pass(sampling ? 1 : 0, kSample, 0);
+            unsigned long long listed = 0;
+            rc = bounds_pass(sampling ? 1 : 0, kSample);
             if (rc) return rc;
-            CU_TRY(cudaMemcpyAsync(probe, ctr + 5, 24, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaMemcpyAsync(&listed, ctr + 5, 8, cudaMemcpyDeviceToHost, s));
             CU_TRY(cudaStreamSynchronize(s));
             long long probed_q = 0;
             for (int t = 0; t < n_tiles_main; t += kSample) probed_q += std::min(tq_main, nq - t * tq_main);
-            const double denom = std::max(1.0, (double)probed_q * n_list_pages);
-            const double kept = (double)probe[0] / denom;      // what the tiles would scan with the bounds they have now
-            const double kept_q = (double)probe[2] / denom;    // what the queries need, one by one
-            // a prefilter page costs ~1/10 of an exact page, so pruning must remove much more before it pays for itself.  Prefilter
-            // scan: the decision looks at the per-query need -- a few queries with a loose seed bound inflate their tiles' unions,
-            // which is exactly what the first pass below repairs.
-            const bool worth = use_tc ? (kept < 0.60 || kept_q < 0.15) : kept < 0.90;
+            const double kept = (double)listed / std::max(1.0, (double)probed_q * n_list_pages);
+            // a prefilter page costs ~1/10 of an exact page, so pruning must remove much more before it pays for itself
+            const bool worth = kept < (use_tc ? 0.60 : 0.90);
             if (!worth) {
                 if (sampling) {
                     rc = list_all(2, kSample);
@@ -454,24 +468,8 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
                 }
             } else {
                 h->sample_streak = 0;
-                pruned = use_tc || kept < 0.5;
-                if (use_tc) {
-                    // Two passes (scht_select.cuh): first every tile scans the super-groups nearest to its queries, which gives
-                    // every query -- also one whose approximate leaf lies in the wrong cluster -- a tight bound; then the bound
-                    // test selects the pages of the main scan for all tiles.
-                    CU_TRY(cudaMemsetAsync(ctr + 5, 0, 8, s));
-                    rc = bounds_pass(0, 1, 1);
-                    if (rc) return rc;
-                    if (timed) CU_TRY(cudaEventRecord(h->ev_fp[0], s));
-                    rc = launch_tc_scan(kWriteState, false);
-                    if (rc) return rc;
-                    if (timed) CU_TRY(cudaEventRecord(h->ev_fp[1], s));
-                    first_pass = true;
-                    CU_TRY(cudaMemsetAsync(ctr + 5, 0, 8, s));
-                    rc = bounds_pass(0, 1, 0);
-                } else if (sampling) {
-                    rc = bounds_pass(2, kSample, 0);
-                }
+                pruned = kept < 0.5;
+                if (sampling) rc = bounds_pass(2, kSample);
             }
             h->sample_sig = sig;
         }
@@ -519,14 +517,7 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             st->ms_seed_scan += b;
             st->ms_main_scan += c2;
             st->ms_traverse += tr;
-            if (first_pass) {
-                float fp = 0;
-                CU_TRY(cudaEventElapsedTime(&fp, h->ev_fp[0], h->ev_fp[1]));
-                st->ms_first_pass += fp;
-                st->ms_traverse -= fp;
-            }
         }
-        st->first_pass_batches += first_pass ? 1 : 0;
     }
     return SCHT_OK;
 }
@@ -739,12 +730,10 @@ extern "C" void scht_destroy(scht_handle* h) {
     if (h->out_stream) cudaStreamSynchronize(h->out_stream);
     for (void* p : h->owned) cudaFree(p);
     for (DevBuf* b : {&h->q[0], &h->q[1], &h->idx[0], &h->idx[1], &h->d2[0], &h->d2[1], &h->dist[0], &h->dist[1], &h->q_leaf, &h->hist, &h->q_order,
-                      &h->state, &h->ranges, &h->n_ranges, &h->counters, &h->seg_keys, &h->ext_bound, &h->bound_own, &h->tmp_keys})
+                      &h->state, &h->ranges, &h->n_ranges, &h->counters, &h->seg_keys, &h->ext_bound, &h->bound_own, &h->sel_bound, &h->tmp_keys})
         b->release();
     for (PinBuf* b : {&h->pin_q[0], &h->pin_q[1], &h->pin_out[0], &h->pin_out[1]}) b->release();
     for (auto& e : h->ev)
-        if (e) cudaEventDestroy(e);
-    for (auto& e : h->ev_fp)
         if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
@@ -802,6 +791,8 @@ extern "C" int scht_set_option(scht_handle* h, const char* name, int64_t value) 
             x->opt.*(e.field) = (int)value;
             x->sample_skip = 0;
             x->sample_streak = 0;
+            x->elig_skip = 0;
+            x->elig_streak = 0;
             if (e.field == &Options::seed_points) {
                 int rc = rebuild_seed_ranges(x);
                 if (rc) return rc;

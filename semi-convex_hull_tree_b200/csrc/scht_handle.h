@@ -91,7 +91,6 @@ struct scht_handle {
     cudaStream_t copy_stream = nullptr;  // H2D of the next batch (scht_query pipeline)
     cudaStream_t out_stream = nullptr;   // D2H of the previous batch
     cudaEvent_t ev[6] = {};
-    cudaEvent_t ev_fp[2] = {};  // first pass of a pruned batch (k_scan_tc over the nearest super-groups)
     cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {};  // per pipeline slot: queries uploaded, kernels done, results downloaded
     scht::DevTree T{};
     scht::ScanImage I{};
@@ -103,13 +102,16 @@ struct scht_handle {
     scht::Options opt;
     int sample_streak = 0, sample_skip = 0;
     long long sample_sig = -1;
+    // the same for the eligibility verdict of the prefilter (tc = 2): two equal verdicts in a row are reused for sample_reuse batches
+    int elig_streak = 0, elig_skip = 0, elig_last = -1;
+    long long elig_sig = -1;
     int64_t tc_batches = 0;
     // state of the batch between batch_seed and batch_main
     struct { int variant = 0, tq = 0, launches = 0, scans = 0, kind = 0, nq = 0, K = 0; } bs;
     std::vector<int> h_leaf_start, h_leaf_count, h_parent;
     std::vector<scht::NodeRec> h_rec;
     scht::DevBuf q[2], idx[2], d2[2], dist[2];  // per pipeline slot
-    scht::DevBuf q_leaf, hist, q_order, state, ranges, n_ranges, counters, seg_keys, ext_bound, bound_own, tmp_keys;
+    scht::DevBuf q_leaf, hist, q_order, state, ranges, n_ranges, counters, seg_keys, ext_bound, bound_own, sel_bound, tmp_keys;
     scht::PinBuf pin_q[2], pin_out[2];
     // ---- multi-GPU handle (scht_create_multi): the plain handles it drives, one per device -----------------
     std::vector<scht_handle*> subs;

@@ -1068,6 +1068,11 @@ __global__ void k_min_bounds(BoundPtrs B, int n, int nq, float* __restrict__ out
     for (int l = 0; l < n; l++) m = fminf(m, B.p[l][i]);
     out[i] = m;
 }
+// dst[i] = src[i] (or FLT_MAX: no external bound)
+__global__ void k_init_bounds(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src ? src[i] : 3.402823466e+38f;
+}
 // keeps only the keys whose position lies in [pos_lo, pos_hi) (order preserved), or empties the lists (pos_hi <= pos_lo)
 __global__ void k_clip_state(uint64_t* __restrict__ state, int nq, int K, int pos_lo, int pos_hi) {
     int slot = blockIdx.x * blockDim.x + threadIdx.x;

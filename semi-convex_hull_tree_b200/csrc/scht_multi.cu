@@ -64,8 +64,6 @@ void add_stats(scht_stats& a, const scht_stats& b) {
     a.ms_seed_scan = std::max(a.ms_seed_scan, b.ms_seed_scan);
     a.ms_traverse = std::max(a.ms_traverse, b.ms_traverse);
     a.ms_main_scan = std::max(a.ms_main_scan, b.ms_main_scan);
-    a.ms_first_pass = std::max(a.ms_first_pass, b.ms_first_pass);
-    a.first_pass_batches = std::max(a.first_pass_batches, b.first_pass_batches);
 }
 
 void split(int64_t n, int parts, std::vector<int64_t>& lo) {

@@ -14,11 +14,12 @@
 // ascending page ranges per tile in the layout PageWalk reads ([kMaxCuts][kJobRanges] flat = kRangeCap ranges); overflow
 // widens the last range (scans more, stays exact).
 //
-// mode kSelNearest (first pass of a pruned batch): no bound test; every query names the super-group whose centre is
-// nearest and, inside it, the two pages whose centres are nearest; the tile scans those pages first.  A query whose approximate leaf lies in
-// the "wrong" cluster has a seed bound several times too large, and one such query would make the whole tile list a
-// large part of the image; after this pass its list holds real neighbours and the bound test of the second pass is tight
-// for every query.
+// Tightening (SelectParams::tighten): before the bound test every query takes the minimum of its seed bound and
+//     min over super-groups with >= K points of  |q - c| + r
+// -- all points of such a ball lie within |q - c| + r of the query, so its K-th neighbour cannot be farther.  A query
+// whose approximate leaf lies in the "wrong" cluster has a seed bound several times too large, and one such query would
+// make its whole tile list a large part of the image; with this bound every query's test is at least as tight as "the
+// nearest cluster-sized ball".  The tightened bound (squared) is also written out for the scan kernel's filter.
 #pragma once
 #include "scht_kernels.cuh"
 
@@ -35,7 +36,8 @@ struct SelectParams {
     int2* ranges;             // [n_tiles][kRangeCap]
     int* n_ranges;            // [n_tiles][kMaxCuts]
     int sel_mode, sel_step;   // tile subset (tile_of_selection)
-    int nearest;              // 1: kSelNearest pass (see above)
+    int tighten;              // 1: tighten every query's bound with the super-group balls first (see above)
+    float* bound_out;         // [nq] by query id, or null: the bound^2 each query's test used (an upper bound of its K-th distance^2)
     unsigned long long* counters;  // [4] ball tests (per query), [5] pages listed x queries, [7] (query, page) pairs that pass the bound test
 };
 
@@ -46,9 +48,9 @@ static_assert(kSuperPages <= 64, "k_select_pages marks the pages of one super-gr
 
 __host__ __device__ inline size_t select_smem_bytes(int dp_regs, int dpad, int n_supers) {
     const int ds = dp_regs > 0 ? dp_regs : dpad;
-    size_t b = (size_t)kSelGroups * ds * 4 + kSelGroups * 4;
+    (void)n_supers;
+    size_t b = (size_t)kSelGroups * ds * 4 + 2 * kSelGroups * 4;
     if (dp_regs == 0) b += (size_t)dpad * kSelQ * 4;
-    b += (size_t)((n_supers + 31) / 32) * 4;  // bitmap of the nearest pass
     return b + 16;
 }
 
@@ -57,7 +59,6 @@ template <int DP>
 __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ unsigned int s_mask;
-    __shared__ unsigned int s_pm[2];  // first pass: page marks of one super-group (kSuperPages <= 64)
     __shared__ int s_nout;
     const DevTree& T = P.T;
     const ScanImage& I = P.I;
@@ -65,8 +66,8 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
     const int DS = DP > 0 ? DP : dpad;                    // staged row length (floats), a multiple of 4
     float* cs = reinterpret_cast<float*>(sel_smem);       // [kSelGroups][DS] staged centres
     float* rs = cs + (size_t)kSelGroups * DS;             // [kSelGroups] staged radii
-    float* qs = rs + kSelGroups;                          // DP == 0: [dpad][kSelQ]
-    unsigned int* near_map = reinterpret_cast<unsigned int*>(qs + (DP > 0 ? 0 : (size_t)dpad * kSelQ));  // [(n_supers+31)/32] bits (nearest pass)
+    int* ns = reinterpret_cast<int*>(rs + kSelGroups);    // [kSelGroups] staged point counts (super-groups)
+    float* qs = reinterpret_cast<float*>(ns + kSelGroups);  // DP == 0: [dpad][kSelQ]
     const int t = threadIdx.x, lane = t & 31;
     const int n_tiles = (P.nq + kSelQ - 1) / kSelQ;
     const int tile = tile_of_selection((int)blockIdx.x, P.sel_mode, P.sel_step);
@@ -129,12 +130,15 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
         return !((dc * (1.f - e) - r * (1.f + e)) > thr);  // NaN / inf never skip
     };
     // stage n balls (rows of `cen`, radii `rad`) starting at index i0
-    auto stage = [&](const float* cen, const float* rad, int i0, int n) {
+    auto stage = [&](const float* cen, const float* rad, const int* cnt, int i0, int n) {
         for (int x = t; x < n * DS; x += kSelQ) {
             const int r = x / DS, j = x - r * DS;
             cs[x] = (j < dpad) ? cen[(size_t)(i0 + r) * dpad + j] : 0.f;
         }
-        if (t < n) rs[t] = rad[i0 + t];
+        if (t < n) {
+            rs[t] = rad[i0 + t];
+            ns[t] = cnt[i0 + t];
+        }
     };
 
     int2* out = P.ranges + (size_t)tile * kRangeCap;
@@ -162,72 +166,25 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
         }
     };
 
-    if (P.nearest) {
-        // ---- first pass: the super-group nearest to each query ----
-        const int n_words = (I.n_supers + 31) / 32;
-        for (int w = t; w < n_words; w += kSelQ) near_map[w] = 0u;
-        float bd = 3.4e38f;
-        int bi = -1;
+    if (P.tighten) {
+        float ub = 3.4e38f;
         for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
             const int ng = min(kSelGroups, I.n_supers - g0);
             __syncthreads();
-            stage(I.scen, I.srad, g0, ng);
+            stage(I.scen, I.srad, I.scnt, g0, ng);
             __syncthreads();
             if (valid)
-                for (int gi = 0; gi < ng; gi++) {
-                    const float d = dist2(cs + (size_t)gi * DS);
-                    if (d < bd) bd = d, bi = g0 + gi;
-                }
+                for (int gi = 0; gi < ng; gi++)
+                    if (ns[gi] >= P.K) ub = fminf(ub, sqrtf(dist2(cs + (size_t)gi * DS)) * (1.f + e) + rs[gi]);
         }
         tests += valid ? (unsigned long long)I.n_supers : 0ull;
-        if (bi >= 0) atomicOr(&near_map[bi >> 5], 1u << (bi & 31));
-        __syncthreads();
-        // the marked super-groups in ascending order; of each, the two pages nearest to every query that chose it
-        for (int w = 0; w < n_words; w++) {
-            unsigned int m = near_map[w];  // block-uniform
-            while (m) {
-                const int sgi = 32 * w + __ffs(m) - 1;
-                m &= m - 1;
-                const int pb = I.spage[sgi], pe = I.spage[sgi + 1];
-                const bool mine = bi == sgi;
-                float d1 = 3.4e38f, d2 = 3.4e38f;
-                int p1 = -1, p2 = -1;
-                for (int p0 = pb; p0 < pe; p0 += kSelPages) {
-                    const int np = min(kSelPages, pe - p0);
-                    __syncthreads();
-                    stage(I.pcen, I.prad, p0, np);
-                    if (t < 2) s_pm[t] = 0u;
-                    __syncthreads();
-                    if (mine)
-                        for (int pi = 0; pi < np; pi++) {
-                            const float d = dist2(cs + (size_t)pi * DS);
-                            if (d < d1) {
-                                d2 = d1, p2 = p1;
-                                d1 = d, p1 = p0 + pi;
-                            } else if (d < d2) {
-                                d2 = d, p2 = p0 + pi;
-                            }
-                        }
-                }
-                if (p1 >= 0) atomicOr(&s_pm[(p1 - pb) >> 5], 1u << ((p1 - pb) & 31));
-                if (p2 >= 0) atomicOr(&s_pm[(p2 - pb) >> 5], 1u << ((p2 - pb) & 31));
-                __syncthreads();
-                if (t == 0)
-                    for (int k = 0; k < 2; k++) {
-                        unsigned int pm = s_pm[k];
-                        while (pm) {
-                            const int pg = pb + 32 * k + __ffs(pm) - 1;
-                            pm &= pm - 1;
-                            add_pages(pg, pg + 1);
-                        }
-                    }
-            }
-        }
-    } else
+        if (valid) thr = fminf(thr, ub * (1.f + e) * (1.f + e) * (1.f + e));
+    }
+    if (P.bound_out && valid) P.bound_out[qid] = fminf(thr * thr, 3.402823466e+38f);
     for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
         const int ng = min(kSelGroups, I.n_supers - g0);
         __syncthreads();  // previous round's readers of cs are done
-        stage(I.scen, I.srad, g0, ng);
+        stage(I.scen, I.srad, I.scnt, g0, ng);
         __syncthreads();
         unsigned int gm = 0;
         if (valid)
@@ -249,7 +206,7 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
             for (int p0 = pb; p0 < pe; p0 += kSelPages) {
                 const int np = min(kSelPages, pe - p0);
                 __syncthreads();  // cs free; s_mask reset visible
-                stage(I.pcen, I.prad, p0, np);
+                stage(I.pcen, I.prad, I.pcnt, p0, np);
                 __syncthreads();
                 unsigned int pm = 0;
                 if (mine)

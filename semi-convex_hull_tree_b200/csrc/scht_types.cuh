@@ -77,6 +77,7 @@ struct ScanImage {
     const float* prad;             // [n_spages] radius (upper bound) around pcen
     const float* scen;             // [n_supers][dpad]
     const float* srad;             // [n_supers]
+    const int* scnt;               // [n_supers] real points of the super-group
     const int* spage;              // [n_supers+1] first page of each super-group
     int n_slots, n_spages, n_supers, n_groups;  // n_slots = n_spages*256 (padding included); n_groups: k-means groups the order was built from
     const float* mean;             // [dpad] centre the image is taken around

@@ -9,8 +9,8 @@ W, F = sys.argv[1], sys.argv[2]
 try:
     l=json.loads(open(F).read().strip().splitlines()[-1])
     s=l["stats_one_step"]; r=l["roofline"]; t=l["tree"]
-    print("%s: value %.3f Mq/s e2e %.3f ms/step %.2f | seed %.2f select %.2f first %.2f main %.2f | scanned/query gpu %.0f ref %s | tc %d | parity %s/%s | create %.2fs supers %d pages %d | clocks %s %s" % (
-        W, l["value"]/1e6, l["e2e"]["value"]/1e6, l["ms_per_step"], s["ms_seed_scan"], s["ms_traverse"], s["ms_first_pass"], s["ms_main_scan"], r["gpu_scanned_points_per_query"],
+    print("%s: value %.3f Mq/s e2e %.3f ms/step %.2f | seed %.2f select %.2f main %.2f | scanned/query gpu %.0f ref %s | tc %d | parity %s/%s | create %.2fs supers %d pages %d | clocks %s %s" % (
+        W, l["value"]/1e6, l["e2e"]["value"]/1e6, l["ms_per_step"], s["ms_seed_scan"], s["ms_traverse"], s["ms_main_scan"], r["gpu_scanned_points_per_query"],
         r["ref_scanned_points_per_query"], s["prefilter_batches"], l.get("parity_mismatches"), l.get("parity_checked"), t["device_create_s"], t["super_groups"], t["scan_pages"],
         l["clocks"]["sm_mhz"], l["clocks"]["reasons"]))
 except Exception as e:
