@@ -469,7 +469,22 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             } else {
                 h->sample_streak = 0;
                 pruned = kept < 0.5;
-                if (sampling) rc = bounds_pass(2, kSample);
+                if (use_tc) {
+                    // Two passes (scht_select.cuh): the queries whose seed bound is worse than the ball bound first scan the two
+                    // nearest pages of their nearest super-group (lists -> state); then the bound test selects the pages of the
+                    // main scan for all tiles with bounds that are tight for every query.
+                    CU_TRY(cudaMemsetAsync(ctr + 5, 0, 8, s));
+                    SP.first_pass = 1;
+                    rc = bounds_pass(0, 1);
+                    if (rc) return rc;
+                    rc = launch_tc_scan(kWriteState, false);
+                    if (rc) return rc;
+                    CU_TRY(cudaMemsetAsync(ctr + 5, 0, 8, s));
+                    SP.first_pass = 0;
+                    rc = bounds_pass(0, 1);
+                } else if (sampling) {
+                    rc = bounds_pass(2, kSample);
+                }
             }
             h->sample_sig = sig;
         }

@@ -20,6 +20,11 @@
 // whose approximate leaf lies in the "wrong" cluster has a seed bound several times too large, and one such query would
 // make its whole tile list a large part of the image; with this bound every query's test is at least as tight as "the
 // nearest cluster-sized ball".  The tightened bound (squared) is also written out for the scan kernel's filter.
+//
+// First pass (SelectParams::first_pass): a query whose seed bound is worse than that ball bound ("loose": its approximate
+// leaf was the wrong place to look) names the two pages nearest to it inside its nearest super-group; the tile scans
+// those few pages first (k_scan_tc, lists -> state), after which the loose queries hold real neighbours and the bound test
+// of the main selection is tight for every query.  Tiles without loose queries list nothing.
 #pragma once
 #include "scht_kernels.cuh"
 
@@ -37,6 +42,7 @@ struct SelectParams {
     int* n_ranges;            // [n_tiles][kMaxCuts]
     int sel_mode, sel_step;   // tile subset (tile_of_selection)
     int tighten;              // 1: tighten every query's bound with the super-group balls first (see above)
+    int first_pass;           // 1: list only the pages the loose queries should scan first (needs tighten)
     float* bound_out;         // [nq] by query id, or null: the bound^2 each query's test used (an upper bound of its K-th distance^2)
     unsigned long long* counters;  // [4] ball tests (per query), [5] pages listed x queries, [7] (query, page) pairs that pass the bound test
 };
@@ -48,9 +54,9 @@ static_assert(kSuperPages <= 64, "k_select_pages marks the pages of one super-gr
 
 __host__ __device__ inline size_t select_smem_bytes(int dp_regs, int dpad, int n_supers) {
     const int ds = dp_regs > 0 ? dp_regs : dpad;
-    (void)n_supers;
     size_t b = (size_t)kSelGroups * ds * 4 + 2 * kSelGroups * 4;
     if (dp_regs == 0) b += (size_t)dpad * kSelQ * 4;
+    b += (size_t)((n_supers + 31) / 32) * 4;  // marks of the first pass
     return b + 16;
 }
 
@@ -59,6 +65,7 @@ template <int DP>
 __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ unsigned int s_mask;
+    __shared__ unsigned int s_pm[2];  // first pass: page marks of one super-group (kSuperPages <= 64)
     __shared__ int s_nout;
     const DevTree& T = P.T;
     const ScanImage& I = P.I;
@@ -68,6 +75,7 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
     float* rs = cs + (size_t)kSelGroups * DS;             // [kSelGroups] staged radii
     int* ns = reinterpret_cast<int*>(rs + kSelGroups);    // [kSelGroups] staged point counts (super-groups)
     float* qs = reinterpret_cast<float*>(ns + kSelGroups);  // DP == 0: [dpad][kSelQ]
+    unsigned int* near_map = reinterpret_cast<unsigned int*>(qs + (DP > 0 ? 0 : (size_t)dpad * kSelQ));  // [(n_supers+31)/32] bits (first pass)
     const int t = threadIdx.x, lane = t & 31;
     const int n_tiles = (P.nq + kSelQ - 1) / kSelQ;
     const int tile = tile_of_selection((int)blockIdx.x, P.sel_mode, P.sel_step);
@@ -166,21 +174,77 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
         }
     };
 
+    bool loose = false;  // the ball bound beats this query's seed bound
+    int near_s = -1;     // super-group with the nearest centre
     if (P.tighten) {
-        float ub = 3.4e38f;
+        float ub = 3.4e38f, bd = 3.4e38f;
         for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
             const int ng = min(kSelGroups, I.n_supers - g0);
             __syncthreads();
             stage(I.scen, I.srad, I.scnt, g0, ng);
             __syncthreads();
             if (valid)
-                for (int gi = 0; gi < ng; gi++)
-                    if (ns[gi] >= P.K) ub = fminf(ub, sqrtf(dist2(cs + (size_t)gi * DS)) * (1.f + e) + rs[gi]);
+                for (int gi = 0; gi < ng; gi++) {
+                    const float d2c = dist2(cs + (size_t)gi * DS);
+                    if (ns[gi] >= P.K) ub = fminf(ub, sqrtf(d2c) * (1.f + e) + rs[gi]);
+                    if (d2c < bd) bd = d2c, near_s = g0 + gi;
+                }
         }
         tests += valid ? (unsigned long long)I.n_supers : 0ull;
-        if (valid) thr = fminf(thr, ub * (1.f + e) * (1.f + e) * (1.f + e));
+        const float ub_thr = ub * (1.f + e) * (1.f + e) * (1.f + e);
+        loose = valid && ub_thr < thr;
+        if (valid) thr = fminf(thr, ub_thr);
     }
-    if (P.bound_out && valid) P.bound_out[qid] = fminf(thr * thr, 3.402823466e+38f);
+    if (P.bound_out && valid && !P.first_pass) P.bound_out[qid] = fminf(thr * thr, 3.402823466e+38f);
+    if (P.first_pass) {
+        // ---- the pages the loose queries scan first: of the nearest super-group of each, its two nearest pages ----
+        const int n_words = (I.n_supers + 31) / 32;
+        __syncthreads();
+        for (int w = t; w < n_words; w += kSelQ) near_map[w] = 0u;
+        __syncthreads();
+        if (loose && near_s >= 0) atomicOr(&near_map[near_s >> 5], 1u << (near_s & 31));
+        __syncthreads();
+        for (int w = 0; w < n_words; w++) {
+            unsigned int m = near_map[w];  // block-uniform
+            while (m) {
+                const int sgi = 32 * w + __ffs(m) - 1;
+                m &= m - 1;
+                const int pb = I.spage[sgi], pe = I.spage[sgi + 1];
+                const bool mine = loose && near_s == sgi;
+                float d1 = 3.4e38f, d2 = 3.4e38f;
+                int p1 = -1, p2 = -1;
+                for (int p0 = pb; p0 < pe; p0 += kSelPages) {
+                    const int np = min(kSelPages, pe - p0);
+                    __syncthreads();
+                    stage(I.pcen, I.prad, I.pcnt, p0, np);
+                    if (t < 2) s_pm[t] = 0u;
+                    __syncthreads();
+                    if (mine)
+                        for (int pi = 0; pi < np; pi++) {
+                            const float d = dist2(cs + (size_t)pi * DS);
+                            if (d < d1) {
+                                d2 = d1, p2 = p1;
+                                d1 = d, p1 = p0 + pi;
+                            } else if (d < d2) {
+                                d2 = d, p2 = p0 + pi;
+                            }
+                        }
+                }
+                if (p1 >= 0) atomicOr(&s_pm[(p1 - pb) >> 5], 1u << ((p1 - pb) & 31));
+                if (p2 >= 0) atomicOr(&s_pm[(p2 - pb) >> 5], 1u << ((p2 - pb) & 31));
+                __syncthreads();
+                if (t == 0)
+                    for (int k = 0; k < 2; k++) {
+                        unsigned int pm = s_pm[k];
+                        while (pm) {
+                            const int pg = pb + 32 * k + __ffs(pm) - 1;
+                            pm &= pm - 1;
+                            add_pages(pg, pg + 1);
+                        }
+                    }
+            }
+        }
+    } else
     for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
         const int ng = min(kSelGroups, I.n_supers - g0);
         __syncthreads();  // previous round's readers of cs are done
