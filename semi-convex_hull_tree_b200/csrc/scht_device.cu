@@ -309,6 +309,7 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
         TC.I = I;
         TC.brute = brute ? 1 : 0;
         TC.n_stages = tc_stages;
+        TC.rescorer_sleep_ns = h->opt.rescorer_sleep_ns;
         // Tail effect: n_tiles CTAs of equal length on n_sm SMs take ceil(n_tiles/n_sm) rounds (782 tiles on 148 SMs: 6 rounds
         // for 5.28 rounds of work).  Splitting every tile's page list into S segments (own CTA each, partial lists merged by
         // k_merge_partial) makes the rounds S times shorter: pick the S <= 8 with the smallest ceil(S*n_tiles/n_sm)/S, charging
@@ -469,12 +470,14 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             } else {
                 h->sample_streak = 0;
                 pruned = kept < 0.5;
-                if (use_tc) {
+                if (use_tc && h->opt.first_pass == 0) {
+                    if (sampling) rc = bounds_pass(2, kSample);
+                } else if (use_tc) {
                     // Two passes (scht_select.cuh): the queries whose seed bound is worse than the ball bound first scan the two
                     // nearest pages of their nearest super-group (lists -> state); then the bound test selects the pages of the
                     // main scan for all tiles with bounds that are tight for every query.
                     CU_TRY(cudaMemsetAsync(ctr + 5, 0, 8, s));
-                    SP.first_pass = 1;
+                    SP.first_pass = h->opt.first_pass;
                     rc = bounds_pass(0, 1);
                     if (rc) return rc;
                     rc = launch_tc_scan(kWriteState, false);
@@ -788,6 +791,8 @@ const OptEntry kOptions[] = {
     {"brute_tc", &Options::brute_tc, 0, 1},
     {"pipeline", &Options::pipeline, 0, 1},
     {"pipeline_split", &Options::pipeline_split, 0, 64},
+    {"rescorer_sleep_ns", &Options::rescorer_sleep_ns, 0, 1000000},
+    {"first_pass", &Options::first_pass, 0, 2},
     {"groups", &Options::groups, -1, 1 << 20},
 };
 }  // namespace

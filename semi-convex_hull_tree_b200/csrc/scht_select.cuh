@@ -42,7 +42,7 @@ struct SelectParams {
     int* n_ranges;            // [n_tiles][kMaxCuts]
     int sel_mode, sel_step;   // tile subset (tile_of_selection)
     int tighten;              // 1: tighten every query's bound with the super-group balls first (see above)
-    int first_pass;           // 1: list only the pages the loose queries should scan first (needs tighten)
+    int first_pass;           // 1: list only the pages the loose queries should scan first (needs tighten); 2: the same for every query
     float* bound_out;         // [nq] by query id, or null: the bound^2 each query's test used (an upper bound of its K-th distance^2)
     unsigned long long* counters;  // [4] ball tests (per query), [5] pages listed x queries, [7] (query, page) pairs that pass the bound test
 };
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
         }
         tests += valid ? (unsigned long long)I.n_supers : 0ull;
         const float ub_thr = ub * (1.f + e) * (1.f + e) * (1.f + e);
-        loose = valid && ub_thr < thr;
+        loose = valid && (ub_thr < thr || P.first_pass == 2);
         if (valid) thr = fminf(thr, ub_thr);
     }
     if (P.bound_out && valid && !P.first_pass) P.bound_out[qid] = fminf(thr * thr, 3.402823466e+38f);

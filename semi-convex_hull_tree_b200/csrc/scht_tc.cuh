@@ -42,9 +42,6 @@ constexpr int kTcEpiWarps = 16;
 constexpr int kTcMaxMmaWarps = 4;  // MMA issuers: 2 (one per page parity; narrow points, one K slice per page) or 4 (one per TMEM buffer)
 __host__ __device__ constexpr int tc_threads(int n_iss) { return (kTcEpiWarps + 1 + n_iss + 4) * 32; }  // + producer, MMA issuers, 4 rescorers
 constexpr int kTcQueueCap = 256;   // ring entries per epilogue warp (power of two)
-#ifndef SCHT_RESCORER_SLEEP_NS
-#define SCHT_RESCORER_SLEEP_NS 4000  // an idle rescorer's pause between polls of its rings
-#endif
 
 struct TcScanParams {
     ScanParams S;            // q, q_order, q_leaf, nq, K, write_mode, pos range, ranges (tile = 128 queries), state, outputs
@@ -57,6 +54,7 @@ struct TcScanParams {
     int n_seg;               // page segments per tile (>= 1): CTA b scans segment b / n_tiles of tile b % n_tiles and, when
     int seg_pages;           //   n_seg > 1, writes its key lists to S.keys_out[segment][query][K] (merged by k_merge_partial);
     int seg_page0;           //   segment s = pages [seg_page0 + s*seg_pages, +seg_pages)
+    int rescorer_sleep_ns;   // an idle rescorer's pause between polls of its rings
     int debug;               // SCHT_TC_PROF builds only: 1 = no pair passes the filter, 2 = also skip the min tree
     long long* trace;        // SCHT_TC_PROF builds: [64 pages][8] clock64 stamps of tile 0 (pages 2000..2063)
 };
@@ -440,11 +438,14 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             __threadfence_block();
             asm volatile("bar.sync %0, 160;" ::"r"(1 + quad) : "memory");  // ... visible to the quadrant's 4 epilogue warps
             for (;;) {
-                // One ROUND takes up to 32 entries from the quadrant's four rings together (lane -> ring by prefix sums of the
-                // available counts): the latency of an exact evaluation (loads + the sequential FP64 chain) is paid once per
-                // round whatever the number of entries, and a single ring rarely holds more than two or three.
-                // Fair when the rings are busy (large K): every ring gets 8 of the 32 lanes first, the rest goes to whoever has
+                // One ROUND takes up to 64 entries from the quadrant's four rings together, two per lane (entry x of the round ->
+                // ring by prefix sums of the available counts): the latency of an exact evaluation (slot -> position lookup, row
+                // loads, the sequential FP64 chain) is paid once per round whatever the number of entries, and a lane's two chains
+                // are independent, so they overlap.  Clustered data makes the rescorers the bottleneck of the kernel (a hundred
+                // or more survivors per query against ~20 on uniform data): 32 entries per round left them latency-bound.
+                // Fair when the rings are busy (large K): every ring gets 16 of the 64 places first, the rest goes to whoever has
                 // more, starting at a ring that rotates from round to round (a starved ring stalls its epilogue warp, hence the MMA).
+                constexpr int kE = 2;
                 bool all_done = true;
                 int head_r[4], n_r[4], avail_r[4], total = 0;
 #pragma unroll
@@ -455,81 +456,109 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                     head_r[i] = v_head[w];
                     avail_r[i] = tail - head_r[i];
                     all_done &= (done != 0) && (avail_r[i] == 0);
-                    n_r[i] = min(avail_r[i], 8);
+                    n_r[i] = min(avail_r[i], 8 * kE);
                     total += n_r[i];
                 }
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int extra = min(avail_r[i] - n_r[i], 32 - total);
+                    const int extra = min(avail_r[i] - n_r[i], 32 * kE - total);
                     n_r[i] += extra;
                     total += extra;
                 }
                 if (total == 0) {
                     if (all_done) break;
-                    __nanosleep(SCHT_RESCORER_SLEEP_NS);  // survivors are rare (~1 per 10 pages and warp): poll seldom, the pipeline warps need the issue slots
+                    __nanosleep((unsigned)TP.rescorer_sleep_ns);  // survivors are rare on uniform data (~1 per 10 pages and warp): poll seldom, the pipeline warps need the issue slots
                     continue;
                 }
                 {
                     __threadfence_block();  // entries below a `tail` were written before it was published
-                    int ri = 0, off = lane;
+                    bool live[kE], cand[kE];
+                    float d2[kE];
+                    int pos[kE], cq[kE];
+                    const float* qq[kE];
 #pragma unroll
-                    for (int i = 0; i < 3; i++)
-                        if (ri == i && off >= n_r[i]) {
-                            off -= n_r[i];
-                            ri = i + 1;
-                        }
-                    const int head = ri == 0 ? head_r[0] : ri == 1 ? head_r[1] : ri == 2 ? head_r[2] : head_r[3];
-                    const int n = total;
-                    const uint64_t* ring = queues + (size_t)(quad + 4 * ((ri + rot) & 3)) * kTcQueueCap;
-                    bool cand = false;
-                    float d2 = 0.f;
-                    int pos = 0, cq = 0;
-                    if (lane < n) {
-                        const uint64_t e = ring[(head + off) & (kTcQueueCap - 1)];
-                        pos = I.slot_pos[(uint32_t)e];  // ring entries name a SLOT of the scan-order image; -1: padding of the last page
-                        cq = (int)(e >> 32);
-                        const float* qq = P.q + (size_t)qids[quad * 32 + cq] * T.dim;  // the query's original coordinates
-                        if (pos < 0) {
-                            d2 = 3.402823466e+38f;  // rejected below
-                            pos = 0;
-                        } else if constexpr (ROWS) {
-                            // wide points: the row-major copy (dpad*4 contiguous bytes; the dim-major pages cost one 32-byte
-                            // sector per coordinate).  Loads first (16 dims at a time), then the sequential reference chain
-                            const float4* pr = reinterpret_cast<const float4*>(T.rows + (size_t)pos * dpad);
-                            prefetch_row(pr, dpad);
-                            for (int j0 = 0; j0 < T.dim; j0 += 16) {
-                                float pv[16], qv[16];
+                    for (int e = 0; e < kE; e++) {
+                        int ri = 0, off = lane + 32 * e;
+                        live[e] = off < total;
 #pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    const float4 x = (j0 + 4 * u < dpad) ? __ldg(pr + (j0 >> 2) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                    pv[4 * u] = x.x, pv[4 * u + 1] = x.y, pv[4 * u + 2] = x.z, pv[4 * u + 3] = x.w;
-                                }
-#pragma unroll
-                                for (int u = 0; u < 16; u++) qv[u] = (j0 + u < T.dim) ? qq[j0 + u] : 0.f;
-#pragma unroll
-                                for (int u = 0; u < 16; u++)
-                                    if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qv[u]);
+                        for (int i = 0; i < 3; i++)
+                            if (ri == i && off >= n_r[i]) {
+                                off -= n_r[i];
+                                ri = i + 1;
                             }
-                        } else {
-                            // narrow points (one 16 KB page slice): the dim-major page the seed scan left in L2
-                            const int pgi = pos / kPage;
-                            const float* pg = T.pages + (size_t)pgi * dpad * kPage + (pos - pgi * kPage);
-                            for (int j0 = 0; j0 < T.dim; j0 += 8) {
-                                float pv[8], qv[8];
+                        const int head = ri == 0 ? head_r[0] : ri == 1 ? head_r[1] : ri == 2 ? head_r[2] : head_r[3];
+                        const uint64_t* ring = queues + (size_t)(quad + 4 * ((ri + rot) & 3)) * kTcQueueCap;
+                        cand[e] = false;
+                        d2[e] = 0.f;
+                        pos[e] = -1;
+                        cq[e] = 0;
+                        qq[e] = P.q;
+                        if (live[e]) {
+                            const uint64_t en = ring[(head + off) & (kTcQueueCap - 1)];
+                            pos[e] = I.slot_pos[(uint32_t)en];  // ring entries name a SLOT of the scan-order image; -1: padding
+                            cq[e] = (int)(en >> 32);
+                            qq[e] = P.q + (size_t)qids[quad * 32 + cq[e]] * T.dim;  // the query's original coordinates
+                            n_exact++;
+                        }
+                    }
+                    if constexpr (ROWS) {
+                        // wide points: the row-major copy (dpad*4 contiguous bytes; the dim-major pages cost one 32-byte sector per
+                        // coordinate).  Loads first (8 dims of both entries), then the two sequential reference chains side by side
+                        const float4* pr[kE];
+#pragma unroll
+                        for (int e = 0; e < kE; e++) {
+                            pr[e] = reinterpret_cast<const float4*>(T.rows + (size_t)max(pos[e], 0) * dpad);
+                            if (pos[e] >= 0) prefetch_row(pr[e], dpad);
+                        }
+                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                            float pv[kE][8], qv[kE][8];
+#pragma unroll
+                            for (int e = 0; e < kE; e++) {
+                                const bool ok = pos[e] >= 0;
+                                const float4 x = ok ? __ldg(pr[e] + (j0 >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 y = (ok && j0 + 4 < dpad) ? __ldg(pr[e] + (j0 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                pv[e][0] = x.x, pv[e][1] = x.y, pv[e][2] = x.z, pv[e][3] = x.w;
+                                pv[e][4] = y.x, pv[e][5] = y.y, pv[e][6] = y.z, pv[e][7] = y.w;
+#pragma unroll
+                                for (int u = 0; u < 8; u++) qv[e][u] = (j0 + u < T.dim) ? qq[e][j0 + u] : 0.f;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (j0 + u < T.dim) {
+#pragma unroll
+                                    for (int e = 0; e < kE; e++) d2[e] = ref_acc_sq(d2[e], pv[e][u] - qv[e][u]);
+                                }
+                        }
+                    } else {
+                        // narrow points (one 16 KB page slice): the dim-major page the seed scan left in L2
+                        const float* pg[kE];
+#pragma unroll
+                        for (int e = 0; e < kE; e++) {
+                            const int pp = max(pos[e], 0), pgi = pp / kPage;
+                            pg[e] = T.pages + (size_t)pgi * dpad * kPage + (pp - pgi * kPage);
+                        }
+                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                            float pv[kE][8], qv[kE][8];
+#pragma unroll
+                            for (int e = 0; e < kE; e++)
 #pragma unroll
                                 for (int u = 0; u < 8; u++) {
-                                    const bool in = j0 + u < T.dim;
-                                    pv[u] = in ? pg[(size_t)(j0 + u) * kPage] : 0.f;
-                                    qv[u] = in ? qq[j0 + u] : 0.f;
+                                    const bool in = j0 + u < T.dim && pos[e] >= 0;
+                                    pv[e][u] = in ? pg[e][(size_t)(j0 + u) * kPage] : 0.f;
+                                    qv[e][u] = in ? qq[e][j0 + u] : 0.f;
                                 }
 #pragma unroll
-                                for (int u = 0; u < 8; u++)
-                                    if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qv[u]);
-                            }
+                            for (int u = 0; u < 8; u++)
+                                if (j0 + u < T.dim) {
+#pragma unroll
+                                    for (int e = 0; e < kE; e++) d2[e] = ref_acc_sq(d2[e], pv[e][u] - qv[e][u]);
+                                }
                         }
-                        n_exact++;
-                        cand = (d2 < 3.402823466e+38f) && (pos >= P.pos_lo) && (pos < P.pos_hi);
-                        if (cand) cand = ((uint64_t)__float_as_uint(d2) << 32) <= lists[(size_t)(quad * 32 + cq) * K + K - 1];
+                    }
+#pragma unroll
+                    for (int e = 0; e < kE; e++) {
+                        cand[e] = live[e] && pos[e] >= 0 && (d2[e] < 3.402823466e+38f) && (pos[e] >= P.pos_lo) && (pos[e] < P.pos_hi);
+                        if (cand[e]) cand[e] = ((uint64_t)__float_as_uint(d2[e]) << 32) <= lists[(size_t)(quad * 32 + cq[e]) * K + K - 1];
                     }
                     __syncwarp();
                     if (lane < 4) {  // the ring slots may be reused (values are in registers now)
@@ -538,18 +567,21 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                     }
                     rot++;
                     __syncwarp();  // ... and every lane reads the new heads in the next round
-                    unsigned m = __ballot_sync(0xffffffffu, cand);
-                    while (m) {
-                        int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        float cd2 = __shfl_sync(0xffffffffu, d2, src);
-                        int cpos = __shfl_sync(0xffffffffu, pos, src);
-                        int ccq = __shfl_sync(0xffffffffu, cq, src);
-                        const int a0 = a0s[quad * 32 + ccq], a1 = a1s[quad * 32 + ccq];
-                        uint32_t low = TP.brute ? (uint32_t)T.orig_idx[cpos] : (((cpos >= a0 && cpos < a1) ? 0u : 0x80000000u) | (uint32_t)cpos);
-                        uint64_t key = ((uint64_t)__float_as_uint(cd2) << 32) | low;
-                        uint64_t* L = lists + (size_t)(quad * 32 + ccq) * K;
-                        if (key < L[K - 1]) n_ins += list_insert(L, K, key, lane);
+#pragma unroll
+                    for (int e = 0; e < kE; e++) {
+                        unsigned m = __ballot_sync(0xffffffffu, cand[e]);
+                        while (m) {
+                            int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            float cd2 = __shfl_sync(0xffffffffu, d2[e], src);
+                            int cpos = __shfl_sync(0xffffffffu, pos[e], src);
+                            int ccq = __shfl_sync(0xffffffffu, cq[e], src);
+                            const int a0 = a0s[quad * 32 + ccq], a1 = a1s[quad * 32 + ccq];
+                            uint32_t low = TP.brute ? (uint32_t)T.orig_idx[cpos] : (((cpos >= a0 && cpos < a1) ? 0u : 0x80000000u) | (uint32_t)cpos);
+                            uint64_t key = ((uint64_t)__float_as_uint(cd2) << 32) | low;
+                            uint64_t* L = lists + (size_t)(quad * 32 + ccq) * K;
+                            if (key < L[K - 1]) n_ins += list_insert(L, K, key, lane);
+                        }
                     }
                     // publish the (possibly) tightened bound of this lane's query
                     v_tq[qi] = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));
