@@ -701,7 +701,7 @@ void options_from_env(Options& o) {
     o.brute_tc = env_int("SCHT_BRUTE_TC", o.brute_tc) != 0;
     o.pipeline = env_int("SCHT_PIPELINE", o.pipeline) != 0;
     o.pipeline_split = std::max(0, env_int("SCHT_PIPELINE_SPLIT", o.pipeline_split));
-    o.first_pass = std::max(0, std::min(2, env_int("SCHT_FIRST_PASS", o.first_pass)));
+    o.first_pass = std::max(-1, std::min(2, env_int("SCHT_FIRST_PASS", o.first_pass)));
     o.rescorer_sleep_ns = std::max(0, env_int("SCHT_RESCORER_SLEEP_NS", o.rescorer_sleep_ns));
 }
 

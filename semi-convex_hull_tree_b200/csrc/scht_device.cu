@@ -470,14 +470,20 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             } else {
                 h->sample_streak = 0;
                 pruned = kept < 0.5;
-                if (use_tc && h->opt.first_pass == 0) {
+                // first pass or not?  auto: when the bound test alone already leaves next to nothing (< 3 % of the pages) a first
+                // pass cannot pay for its extra selection and launch; otherwise all queries take it (short lists) or only the loose
+                // ones (K > 32, where the convergence of the lists is the expensive part).  Measured on the BASELINE workloads,
+                // profiles/r02_first_pass.md.
+                int fp = h->opt.first_pass;
+                if (fp < 0) fp = kept < 0.03 ? 0 : (K <= 32 ? 2 : 1);
+                if (use_tc && fp == 0) {
                     if (sampling) rc = bounds_pass(2, kSample);
                 } else if (use_tc) {
                     // Two passes (scht_select.cuh): the queries whose seed bound is worse than the ball bound first scan the two
                     // nearest pages of their nearest super-group (lists -> state); then the bound test selects the pages of the
                     // main scan for all tiles with bounds that are tight for every query.
                     CU_TRY(cudaMemsetAsync(ctr + 5, 0, 8, s));
-                    SP.first_pass = h->opt.first_pass;
+                    SP.first_pass = fp;
                     rc = bounds_pass(0, 1);
                     if (rc) return rc;
                     rc = launch_tc_scan(kWriteState, false);
@@ -792,7 +798,7 @@ const OptEntry kOptions[] = {
     {"pipeline", &Options::pipeline, 0, 1},
     {"pipeline_split", &Options::pipeline_split, 0, 64},
     {"rescorer_sleep_ns", &Options::rescorer_sleep_ns, 0, 1000000},
-    {"first_pass", &Options::first_pass, 0, 2},
+    {"first_pass", &Options::first_pass, -1, 2},
     {"groups", &Options::groups, -1, 1 << 20},
 };
 }  // namespace

@@ -83,7 +83,7 @@ struct Options {
     int brute_tc = 1;           // brute-force entry through the prefilter when eligible (0: exact FP32 scan only)
     int pipeline = 1;           // overlap H2D / kernels / D2H of consecutive batches of one scht_query call
     int rescorer_sleep_ns = SCHT_RESCORER_SLEEP_NS_DEFAULT;  // k_scan_tc: an idle rescorer warp's pause between polls (1500 and 8000 measured equal on uniform data)
-    int first_pass = 1;         // pruned prefilter batches: 0 = bound test only, 1 = queries with a loose seed bound scan their nearest pages first, 2 = all queries do
+    int first_pass = -1;        // pruned prefilter batches: 0 = bound test only, 1 = queries with a loose seed bound scan their nearest pages first, 2 = all queries do, -1 = auto
     int pipeline_split = 0;     // split a single-batch scht_query call into this many sub-batches so that its copies overlap (0/1: off)
 };
 

@@ -438,14 +438,14 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             __threadfence_block();
             asm volatile("bar.sync %0, 160;" ::"r"(1 + quad) : "memory");  // ... visible to the quadrant's 4 epilogue warps
             for (;;) {
-                // One ROUND takes up to 64 entries from the quadrant's four rings together, two per lane (entry x of the round ->
+                // One ROUND takes up to 32 kE entries from the quadrant's four rings together, kE per lane (entry x of the round ->
                 // ring by prefix sums of the available counts): the latency of an exact evaluation (slot -> position lookup, row
                 // loads, the sequential FP64 chain) is paid once per round whatever the number of entries, and a lane's two chains
                 // are independent, so they overlap.  Clustered data makes the rescorers the bottleneck of the kernel (a hundred
                 // or more survivors per query against ~20 on uniform data): 32 entries per round left them latency-bound.
                 // Fair when the rings are busy (large K): every ring gets 16 of the 64 places first, the rest goes to whoever has
                 // more, starting at a ring that rotates from round to round (a starved ring stalls its epilogue warp, hence the MMA).
-                constexpr int kE = 2;
+                constexpr int kE = ROWS ? 2 : 1;  // (narrow points, i.e. the uniform 16-D benchmark, have ~20 survivors per query: one entry per lane, 2 % faster there)
                 bool all_done = true;
                 int head_r[4], n_r[4], avail_r[4], total = 0;
 #pragma unroll
