@@ -318,6 +318,22 @@ __global__ void __launch_bounds__(256) k_group_radii(DevTree T, const unsigned l
     if (threadIdx.x == 0) grad[g] = sqrtf(m);
 }
 
+// exact coordinates, row-major, in scan order (one thread per (slot, 4 dims))
+__global__ void k_build_srows(DevTree T, const int* __restrict__ slot_pos, long long n_slots, float* __restrict__ srows) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q4 = T.dpad >> 2;
+    if (i >= n_slots * q4) return;
+    const long long slot = i / q4;
+    const int j = (int)(i - slot * q4) * 4;
+    const int pos = slot_pos[slot];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos >= 0) {
+        if (T.rows) v = *reinterpret_cast<const float4*>(T.rows + (size_t)pos * T.dpad + j);
+        else v = make_float4(page_coord(T, pos, j), page_coord(T, pos, j + 1), page_coord(T, pos, j + 2), page_coord(T, pos, j + 3));
+    }
+    *reinterpret_cast<float4*>(srows + (size_t)slot * T.dpad + j) = v;
+}
+
 // -------------------------------------------------------------------------------------------------------------
 // tensor-core page image in SCAN order (one thread per slot): row r of scan page sp holds fp16(s (p_j - mean_j)) and, in
 // three extra K slots, s^2 |p - mean|^2 / u as an exact hi + mid + lo FP16 split (see scht_tc.cuh)
@@ -474,7 +490,7 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
     const int kp = (dim + 3 + 15) & ~15;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    if ((size_t)((double)n * 1.1 / kPage + 2) * tc_page_bytes(kp) + (size_t)n * 28 >= free_b / 2) return SCHT_OK;  // no room for the image: the exact FP32 scan serves every batch
+    if ((size_t)((double)n * 1.1 / kPage + 2) * (tc_page_bytes(kp) + (size_t)kPage * dpad * 4) + (size_t)n * 28 >= free_b / 2) return SCHT_OK;  // no room for the image: the exact FP32 scan serves every batch
 
     double amax_all = 0, asum = 0;
     for (int j = 0; j < dim; j++) {
@@ -621,7 +637,7 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
         if (p == n_spages || hard[p] || p - spage_h.back() >= kSuperPages) spage_h.push_back(p);
     const int S = (int)spage_h.size() - 1;
 
-    float *pcen = nullptr, *prad = nullptr, *scen = nullptr, *srad = nullptr;
+    float *pcen = nullptr, *prad = nullptr, *scen = nullptr, *srad = nullptr, *srows = nullptr;
     int *pcnt = nullptr, *spage = nullptr, *scnt = nullptr;
     unsigned char* tcp = nullptr;
     TRY_T(dev_alloc(h, (size_t)n_spages * dpad, &pcen));
@@ -632,8 +648,10 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
     TRY_T(dev_alloc(h, (size_t)S + 1, &spage));
     TRY_T(dev_alloc(h, (size_t)S, &scnt));
     TRY_T(dev_alloc(h, (size_t)n_spages * tc_page_bytes(kp), &tcp));
+    TRY_T(dev_alloc(h, (size_t)n_spages * kPage * dpad, &srows));
     CU_T(cudaMemcpyAsync(spage, spage_h.data(), (size_t)(S + 1) * 4, cudaMemcpyHostToDevice, s));
     k_build_tcpages<<<(unsigned)(((size_t)n_spages * kPage + 255) / 256), 256, 0, s>>>(T, slot_pos, n_spages, d_mean, I.scale, I.norm_unit, kp, tcp);
+    k_build_srows<<<(unsigned)(((size_t)n_spages * kPage * (dpad >> 2) + 255) / 256), 256, 0, s>>>(T, slot_pos, (long long)n_spages * kPage, srows);
     k_page_balls<<<n_spages, 256, dpad * sizeof(float), s>>>(T, slot_pos, pcen, prad, pcnt);
     k_run_balls<<<S, 256, dpad * sizeof(float), s>>>(T, slot_pos, spage, kPage, scen, srad, scnt);
     CU_T(cudaGetLastError());
@@ -666,6 +684,7 @@ int build_scan_image(scht_handle* h, const float* d_mean, const std::vector<floa
     CU_TRY(cudaMemcpy(const_cast<int*>(T.leaf_rank), rank.data(), (size_t)T.n_leaves * 4, cudaMemcpyHostToDevice));
     I.tcpages = tcp;
     I.slot_pos = slot_pos;
+    I.srows = srows;
     I.pcnt = pcnt;
     I.pcen = pcen;
     I.prad = prad;

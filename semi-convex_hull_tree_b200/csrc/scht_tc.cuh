@@ -168,8 +168,8 @@ __device__ __forceinline__ float fmin2f(float a, float b) {
     return d;
 }
 // N_ISS = MMA issuer warps: 2 (23 warps: 80 registers per thread, the min trees keep their values in registers) or 4 (25 warps, 72)
-// ROWS = the rescorers read wide points from the row-major copy (T.rows); a compile-time choice because the pipeline is
-// sensitive to the kernel's code size (both paths in one kernel cost 2.5 % on 16-dimensional points)
+// ROWS = wide points (more than one 16-dimension slice): the rescorers take two ring entries per lane and round instead of one
+// (a compile-time choice because the pipeline is sensitive to the kernel's code size and register count: +2 % on 16-dimensional points)
 // N256 (two issuers only) = one N=256 MMA chain per page instead of two N=128 chains (128 instead of 2 x 92 cycles per K16
 // step): both half-page buffers of the page's parity are filled and committed together; the epilogue is unchanged
 template <int N_ISS, bool ROWS, bool N256>
@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                     float d2[kE];
                     int pos[kE], cq[kE];
                     const float* qq[kE];
+                    const float4* pr[kE];
 #pragma unroll
                     for (int e = 0; e < kE; e++) {
                         int ri = 0, off = lane + 32 * e;
@@ -493,67 +494,38 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                         pos[e] = -1;
                         cq[e] = 0;
                         qq[e] = P.q;
+                        pr[e] = reinterpret_cast<const float4*>(I.srows);
                         if (live[e]) {
                             const uint64_t en = ring[(head + off) & (kTcQueueCap - 1)];
-                            pos[e] = I.slot_pos[(uint32_t)en];  // ring entries name a SLOT of the scan-order image; -1: padding
+                            const uint32_t slot = (uint32_t)en;  // ring entries name a SLOT of the scan-order image
+                            // the survivor's exact coordinates: row-major in scan order, so the row loads do not wait for the
+                            // slot -> position lookup (both go out together; the position is only needed for the key)
+                            pr[e] = reinterpret_cast<const float4*>(I.srows + (size_t)slot * dpad);
+                            prefetch_row(pr[e], dpad);
+                            pos[e] = I.slot_pos[slot];  // -1: padding
                             cq[e] = (int)(en >> 32);
                             qq[e] = P.q + (size_t)qids[quad * 32 + cq[e]] * T.dim;  // the query's original coordinates
                             n_exact++;
                         }
                     }
-                    if constexpr (ROWS) {
-                        // wide points: the row-major copy (dpad*4 contiguous bytes; the dim-major pages cost one 32-byte sector per
-                        // coordinate).  Loads first (8 dims of both entries), then the two sequential reference chains side by side
-                        const float4* pr[kE];
+                    // loads first (8 dims of every entry), then the sequential reference chains side by side
+                    for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                        float pv[kE][8], qv[kE][8];
 #pragma unroll
                         for (int e = 0; e < kE; e++) {
-                            pr[e] = reinterpret_cast<const float4*>(T.rows + (size_t)max(pos[e], 0) * dpad);
-                            if (pos[e] >= 0) prefetch_row(pr[e], dpad);
+                            const float4 x = live[e] ? __ldg(pr[e] + (j0 >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 y = (live[e] && j0 + 4 < dpad) ? __ldg(pr[e] + (j0 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            pv[e][0] = x.x, pv[e][1] = x.y, pv[e][2] = x.z, pv[e][3] = x.w;
+                            pv[e][4] = y.x, pv[e][5] = y.y, pv[e][6] = y.z, pv[e][7] = y.w;
+#pragma unroll
+                            for (int u = 0; u < 8; u++) qv[e][u] = (j0 + u < T.dim) ? qq[e][j0 + u] : 0.f;
                         }
-                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
-                            float pv[kE][8], qv[kE][8];
 #pragma unroll
-                            for (int e = 0; e < kE; e++) {
-                                const bool ok = pos[e] >= 0;
-                                const float4 x = ok ? __ldg(pr[e] + (j0 >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                const float4 y = (ok && j0 + 4 < dpad) ? __ldg(pr[e] + (j0 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                pv[e][0] = x.x, pv[e][1] = x.y, pv[e][2] = x.z, pv[e][3] = x.w;
-                                pv[e][4] = y.x, pv[e][5] = y.y, pv[e][6] = y.z, pv[e][7] = y.w;
+                        for (int u = 0; u < 8; u++)
+                            if (j0 + u < T.dim) {
 #pragma unroll
-                                for (int u = 0; u < 8; u++) qv[e][u] = (j0 + u < T.dim) ? qq[e][j0 + u] : 0.f;
+                                for (int e = 0; e < kE; e++) d2[e] = ref_acc_sq(d2[e], pv[e][u] - qv[e][u]);
                             }
-#pragma unroll
-                            for (int u = 0; u < 8; u++)
-                                if (j0 + u < T.dim) {
-#pragma unroll
-                                    for (int e = 0; e < kE; e++) d2[e] = ref_acc_sq(d2[e], pv[e][u] - qv[e][u]);
-                                }
-                        }
-                    } else {
-                        // narrow points (one 16 KB page slice): the dim-major page the seed scan left in L2
-                        const float* pg[kE];
-#pragma unroll
-                        for (int e = 0; e < kE; e++) {
-                            const int pp = max(pos[e], 0), pgi = pp / kPage;
-                            pg[e] = T.pages + (size_t)pgi * dpad * kPage + (pp - pgi * kPage);
-                        }
-                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
-                            float pv[kE][8], qv[kE][8];
-#pragma unroll
-                            for (int e = 0; e < kE; e++)
-#pragma unroll
-                                for (int u = 0; u < 8; u++) {
-                                    const bool in = j0 + u < T.dim && pos[e] >= 0;
-                                    pv[e][u] = in ? pg[e][(size_t)(j0 + u) * kPage] : 0.f;
-                                    qv[e][u] = in ? qq[e][j0 + u] : 0.f;
-                                }
-#pragma unroll
-                            for (int u = 0; u < 8; u++)
-                                if (j0 + u < T.dim) {
-#pragma unroll
-                                    for (int e = 0; e < kE; e++) d2[e] = ref_acc_sq(d2[e], pv[e][u] - qv[e][u]);
-                                }
-                        }
                     }
 #pragma unroll
                     for (int e = 0; e < kE; e++) {
@@ -632,7 +604,8 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             uint64_t* myq = queues + (size_t)warp * kTcQueueCap;
             volatile int* v_head = q_head + warp;
             volatile float* v_tq = tq_s + qi;
-            int resv = 0;  // ring slots reserved and published by this warp so far (warp-uniform)
+            int resv = 0;  // ring slots written by this warp so far (warp-uniform)
+            int head_cache = 0;  // last value of the rescorer's head this warp has seen (warp-uniform; only re-read when the ring looks full)
             unsigned long long n_pairs = 0;
             asm volatile("bar.sync %0, 160;" ::"r"(1 + quad) : "memory");  // the rescorer has published the initial bounds
             float Tq = *v_tq;
@@ -667,31 +640,37 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                             }
                         }
                     }
-                    // One round if the ring has room for everything (the common case: a handful of survivors); otherwise four
-                    // rounds of 8 columns (<= 256 = kTcQueueCap entries each).  The whole warp waits for room BEFORE any lane
-                    // reserves, so a full ring can always drain (only published entries are consumed).
-                    const int total_all = __reduce_add_sync(0xffffffffu, __popc(mask));
-                    const bool one_round = resv + total_all - *v_head <= kTcQueueCap;
-                    for (int h = 0; h < (one_round ? 1 : 4); h++) {
-                        uint32_t mq = one_round ? mask : (mask & (0xffu << (8 * h)));
-                        const int cnt = __popc(mq);
-                        const int total = one_round ? total_all : __reduce_add_sync(0xffffffffu, cnt);
-                        if (total == 0) continue;
-                        while (resv + total - *v_head > kTcQueueCap) __nanosleep(40);
-                        if (cnt) {
-                            int slot = atomicAdd(q_resv + warp, cnt);
-                            while (mq) {
-                                const int c = __ffs(mq) - 1;
-                                mq &= mq - 1;
-                                myq[(slot++) & (kTcQueueCap - 1)] = ((uint64_t)(uint32_t)lane << 32) | (uint32_t)(page * kPage + col0 + c);
+                    // Ballot rounds: in every round each lane that still has a survivor pushes one; its ring slot is its rank among
+                    // those lanes (no atomic: the warp is the ring's only producer and `resv` is warp-uniform).  A handful of survivors
+                    // take one or two rounds.  Only published entries are consumed, so before the warp waits for room it publishes
+                    // what it has written (a full ring can always drain).  On clustered data nearly every 32-column group of a cluster
+                    // page has a survivor, and this branch -- it used to hold a shared-memory atomic with its round trip, a second
+                    // warp-wide reduction and two more warp barriers -- set the pace of the whole kernel there.
+                    for (;;) {
+                        const unsigned b = __ballot_sync(0xffffffffu, mask != 0);
+                        if (!b) break;
+                        const int n = __popc(b);
+                        if (resv + n - head_cache > kTcQueueCap) {
+                            __syncwarp();
+                            __threadfence_block();
+                            if (lane == 0) *reinterpret_cast<volatile int*>(q_tail + warp) = resv;
+                            for (;;) {
+                                head_cache = __shfl_sync(0xffffffffu, *v_head, 0);
+                                if (resv + n - head_cache <= kTcQueueCap) break;
+                                __nanosleep(40);
                             }
                         }
-                        __syncwarp();
-                        __threadfence_block();
-                        resv += total;
-                        if (lane == 0) *reinterpret_cast<volatile int*>(q_tail + warp) = resv;  // publish for the rescorer
-                        __syncwarp();
+                        if (mask) {
+                            const int c = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const int slot = resv + __popc(b & ((1u << lane) - 1u));
+                            myq[slot & (kTcQueueCap - 1)] = ((uint64_t)(uint32_t)lane << 32) | (uint32_t)(page * kPage + col0 + c);
+                        }
+                        resv += n;
                     }
+                    __syncwarp();
+                    __threadfence_block();
+                    if (lane == 0) *reinterpret_cast<volatile int*>(q_tail + warp) = resv;  // publish for the rescorer
                 }
             };
 

@@ -72,6 +72,8 @@ constexpr int kSuperPages = 64;   // (the first-pass page marks of k_select_page
 struct ScanImage {
     const unsigned char* tcpages;  // per scan page: FP16 image [kp/8][32][8][8] (kp*512 B): s p'_j, then norm hi/mid/lo
     const int* slot_pos;           // [n_spages*256] sorted position of a slot, -1 on padding
+    const float* srows;            // [n_spages*256][dpad] the exact coordinates row-major in SCAN order (zeros on padding): a rescorer reads
+                                   //   one survivor's row straight from its slot, without first looking up the position
     const int* pcnt;               // [n_spages] real points of the page
     const float* pcen;             // [n_spages][dpad] centre of the page's points
     const float* prad;             // [n_spages] radius (upper bound) around pcen
