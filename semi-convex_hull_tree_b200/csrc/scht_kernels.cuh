@@ -133,11 +133,22 @@ __global__ void k_descend(DevTree T, const float* __restrict__ q, int nq, int* _
     while (nr.leaf < 0) {
         const float* lc = T.node_lc + (size_t)node * T.dpad;
         const float* rc = T.node_rc + (size_t)node * T.dpad;
+        // Only the COMPARISON has to be the reference's.  A plain FP32 FMA chain is within (dim + 2) 2^-24 (relative) of the
+        // reference's value (same differences, same order, one rounding per step instead of the float(double) step), so when
+        // the two distances differ by more than 2^-14 of their sum the outcome is certain; near-ties take the exact arithmetic.
         float l = 0.f, r = 0.f;
         for (int j = 0; j < T.dim; j++) {
-            float x = qi[j];
-            l = ref_acc_sq(l, x - lc[j]);
-            r = ref_acc_sq(r, x - rc[j]);
+            const float x = qi[j], dl = x - lc[j], dr = x - rc[j];
+            l = fmaf(dl, dl, l);
+            r = fmaf(dr, dr, r);
+        }
+        if (!(fabsf(l - r) > 6.1035156e-5f * (l + r)) || T.dim > 1024) {
+            l = 0.f, r = 0.f;
+            for (int j = 0; j < T.dim; j++) {
+                float x = qi[j];
+                l = ref_acc_sq(l, x - lc[j]);
+                r = ref_acc_sq(r, x - rc[j]);
+            }
         }
         node = (l >= r) ? nr.right : node + 1;  // ties go right (Code/CPU_Convex_Tree.h:191)
         nr = T.nodes[node];
