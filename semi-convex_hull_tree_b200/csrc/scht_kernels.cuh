@@ -647,70 +647,83 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
                     if (qi < 4) cm_lo |= b << (8 * qi + 2 * pp);
                     else cm_hi |= b << (8 * (qi - 4) + 2 * pp);
                 }
-            float new_thr[kQPerWarp];
+            // Exact path.  One ROUND: every lane re-evaluates ONE of its own candidates -- of whichever of the warp's 8 queries --
+            // with the reference arithmetic; then the round's results are inserted query by query.  Pooling the queries matters
+            // because the latency of an evaluation (row loads + the sequential FP64 chain) is paid once per round whatever the
+            // number of busy lanes: a page leaves ~15 candidates per query, i.e. one or two rounds per query taken one query at a
+            // time (8-16 rounds per page and warp), but only max-per-lane ~ 5-7 rounds when the 64 (query, point) bits of a lane
+            // are drained together.
+            uint64_t cm = ((uint64_t)cm_hi << 32) | cm_lo;
 #pragma unroll 1
-            for (int qi = 0; qi < kQPerWarp; qi++) {
-                uint32_t bits = ((qi < 4 ? cm_lo : cm_hi) >> (8 * (qi & 3))) & 0xffu;
-                uint64_t* L = my_lists + (size_t)qi * K;
-                if (__any_sync(0xffffffffu, bits != 0)) {
-                    const int a0 = a0s[qw0 + qi], a1 = a1s[qw0 + qi];
-                    do {
-                        // every lane re-evaluates one of its own candidates with the reference arithmetic
-                        bool cand = false;
-                        float d2 = 0.f;
-                        int pos = 0;
-                        if (bits) {
-                            int e = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            int in_page = ((e >> 2) ? 128 : 0) + 4 * lane + (e & 3);
-                            pos = page * kPage + in_page;
-                            const float* qq = qs + qw0 + qi;
-                            // loads first (8 dims in flight), then the sequential reference chain: the chain would otherwise
-                            // serialise one round trip per dimension.  A held stage is read from shared memory (dim-major);
-                            // otherwise the point's row comes from the row-major copy (two 16-byte loads per 8 dims)
-                            if (hold_stage) {
-                                const float* pg = stage_mem + (size_t)held_st * kRowsPerStage * kPage + in_page;
-                                for (int j0 = 0; j0 < T.dim; j0 += 8) {
-                                    float pv[8];
+            while (__any_sync(0xffffffffu, cm != 0)) {
+                bool cand = false;
+                float d2 = 0.f;
+                int pos = 0, cqi = -1;
+                if (cm) {
+                    const int b = __ffsll((long long)cm) - 1;
+                    cm &= cm - 1;
+                    cqi = b >> 3;
+                    const int e = b & 7;
+                    const int in_page = ((e >> 2) ? 128 : 0) + 4 * lane + (e & 3);
+                    pos = page * kPage + in_page;
+                    const float* qq = qs + qw0 + cqi;
+                    // loads first (8 dims in flight), then the sequential reference chain: the chain would otherwise
+                    // serialise one round trip per dimension.  A held stage is read from shared memory (dim-major);
+                    // otherwise the point's row comes from the row-major copy (two 16-byte loads per 8 dims)
+                    if (hold_stage) {
+                        const float* pg = stage_mem + (size_t)held_st * kRowsPerStage * kPage + in_page;
+                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                            float pv[8];
 #pragma unroll
-                                    for (int u = 0; u < 8; u++) pv[u] = (j0 + u < T.dim) ? pg[(size_t)(j0 + u) * kPage] : 0.f;
+                            for (int u = 0; u < 8; u++) pv[u] = (j0 + u < T.dim) ? pg[(size_t)(j0 + u) * kPage] : 0.f;
 #pragma unroll
-                                    for (int u = 0; u < 8; u++)
-                                        if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
-                                }
-                            } else {
-                                const float4* pr = reinterpret_cast<const float4*>(T.rows + (size_t)pos * dpad);
-                                prefetch_row(pr, dpad);
-                                for (int j0 = 0; j0 < T.dim; j0 += 8) {
-                                    const float4 x = __ldg(pr + (j0 >> 2));
-                                    const float4 y = (j0 + 4 < dpad) ? __ldg(pr + (j0 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                    const float pv[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-#pragma unroll
-                                    for (int u = 0; u < 8; u++)
-                                        if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
-                                }
-                            }
-                            n_exact++;
-                            cand = (d2 < 3.402823466e+38f) && (pos >= P.pos_lo) && (pos < P.pos_hi);
+                            for (int u = 0; u < 8; u++)
+                                if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
                         }
-                        // Smallest first: each round takes the warp-minimum key of the remaining candidates (two REDUX).  As soon as
-                        // the minimum cannot enter the list none of the others can, so rejected candidates cost nothing (while the
-                        // lists are still filling, most candidates of a batch are rejected by the ones inserted before them).
-                        uint32_t hi = cand ? __float_as_uint(d2) : 0xffffffffu;  // valid d2 bits are < 0x7f7fffff
-                        uint32_t low = 0xffffffffu;
-                        if (cand) low = brute ? (uint32_t)T.orig_idx[pos] : (((pos >= a0 && pos < a1) ? 0u : 0x80000000u) | (uint32_t)pos);
-                        for (;;) {
-                            const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
-                            if (mhi == 0xffffffffu) break;
-                            const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? low : 0xffffffffu);
-                            const uint64_t key = ((uint64_t)mhi << 32) | mlo;
-                            if (key >= L[K - 1]) break;  // nothing smaller is left
-                            n_ins += list_insert(L, K, key, lane);
-                            if (hi == mhi && low == mlo) hi = 0xffffffffu;  // consumed (keys are unique)
+                    } else {
+                        const float4* pr = reinterpret_cast<const float4*>(T.rows + (size_t)pos * dpad);
+                        prefetch_row(pr, dpad);
+                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                            const float4 x = __ldg(pr + (j0 >> 2));
+                            const float4 y = (j0 + 4 < dpad) ? __ldg(pr + (j0 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float pv[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
                         }
-                    } while (__any_sync(0xffffffffu, bits != 0));
+                    }
+                    n_exact++;
+                    cand = (d2 < 3.402823466e+38f) && (pos >= P.pos_lo) && (pos < P.pos_hi);
                 }
-                float kth = __uint_as_float((uint32_t)(L[K - 1] >> 32));
+                uint32_t low = 0xffffffffu;
+                if (cand) {
+                    const int a0 = a0s[qw0 + cqi], a1 = a1s[qw0 + cqi];
+                    low = brute ? (uint32_t)T.orig_idx[pos] : (((pos >= a0 && pos < a1) ? 0u : 0x80000000u) | (uint32_t)pos);
+                }
+                // the round's results, query by query.  Smallest first: each step takes the warp-minimum key of the query's remaining
+                // candidates (two REDUX); as soon as the minimum cannot enter the list none of the others can, so rejected candidates
+                // cost nothing (while the lists are still filling, most candidates are rejected by the ones inserted before them).
+#pragma unroll 1
+                for (int qi = 0; qi < kQPerWarp; qi++) {
+                    const bool mine = cand && cqi == qi;
+                    if (!__any_sync(0xffffffffu, mine)) continue;
+                    uint64_t* L = my_lists + (size_t)qi * K;
+                    uint32_t hi = mine ? __float_as_uint(d2) : 0xffffffffu;  // valid d2 bits are < 0x7f7fffff
+                    for (;;) {
+                        const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+                        if (mhi == 0xffffffffu) break;
+                        const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? low : 0xffffffffu);
+                        const uint64_t key = ((uint64_t)mhi << 32) | mlo;
+                        if (key >= L[K - 1]) break;  // nothing smaller is left
+                        n_ins += list_insert(L, K, key, lane);
+                        if (hi == mhi && low == mlo) hi = 0xffffffffu;  // consumed (keys are unique)
+                    }
+                }
+            }
+            float new_thr[kQPerWarp];
+#pragma unroll
+            for (int qi = 0; qi < kQPerWarp; qi++) {
+                const float kth = __uint_as_float((uint32_t)(my_lists[(size_t)qi * K + K - 1] >> 32));
                 new_thr[qi] = (qw0 + qi < nq_tile) ? fminf(fminf(kth * 1.000001f, 3.402823466e+38f), exts[qw0 + qi]) : -1.f;
             }
 #pragma unroll
