@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
     float* rs = cs + (size_t)kSelGroups * DS;             // [kSelGroups] staged radii
     int* ns = reinterpret_cast<int*>(rs + kSelGroups);    // [kSelGroups] staged point counts (super-groups)
     float* qs = reinterpret_cast<float*>(ns + kSelGroups);  // DP == 0: [dpad][kSelQ]
-    unsigned int* near_map = reinterpret_cast<unsigned int*>(qs + (DP > 0 ? 0 : (size_t)dpad * kSelQ));  // [(n_supers+31)/32] bits (first pass)
+    unsigned int* near_map = reinterpret_cast<unsigned int*>(qs + (DP > 0 ? 0 : (size_t)dpad * kSelQ));  // [(n_supers+31)/32] bits: candidates of the test loop / marks of the first pass
     const int t = threadIdx.x, lane = t & 31;
     const int n_tiles = (P.nq + kSelQ - 1) / kSelQ;
     const int tile = tile_of_selection((int)blockIdx.x, P.sel_mode, P.sel_step);
@@ -176,29 +176,41 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
 
     bool loose = false;  // the ball bound beats this query's seed bound
     int near_s = -1;     // super-group with the nearest centre
+    // cand_map: bit per super-group, set when some query of the tile could not rule it out with the bound it had at the time (its
+    // seed bound, tightened along the way): the test loop below only revisits those.  Without tightening: all set.
+    const int n_words = (I.n_supers + 31) / 32;
+    for (int w = t; w < n_words; w += kSelQ) near_map[w] = P.tighten ? 0u : 0xffffffffu;
     if (P.tighten) {
-        float ub = 3.4e38f, bd = 3.4e38f;
+        float ub = 3.4e38f, bd = 3.4e38f, run_thr = thr;
         for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
             const int ng = min(kSelGroups, I.n_supers - g0);
             __syncthreads();
             stage(I.scen, I.srad, I.scnt, g0, ng);
             __syncthreads();
+            unsigned int cm = 0;
             if (valid)
                 for (int gi = 0; gi < ng; gi++) {
                     const float d2c = dist2(cs + (size_t)gi * DS);
-                    if (ns[gi] >= P.K) ub = fminf(ub, sqrtf(d2c) * (1.f + e) + rs[gi]);
+                    const float dc = sqrtf(d2c);
+                    if (ns[gi] >= P.K) {
+                        ub = fminf(ub, dc * (1.f + e) + rs[gi]);
+                        run_thr = fminf(run_thr, ub * (1.f + e) * (1.f + e) * (1.f + e));
+                    }
                     if (d2c < bd) bd = d2c, near_s = g0 + gi;
+                    if (!((dc * (1.f - e) - rs[gi] * (1.f + e)) > run_thr)) cm |= 1u << gi;
                 }
+            cm = __reduce_or_sync(0xffffffffu, cm);
+            if (lane == 0 && cm) atomicOr(&near_map[g0 >> 5], cm);
         }
         tests += valid ? (unsigned long long)I.n_supers : 0ull;
         const float ub_thr = ub * (1.f + e) * (1.f + e) * (1.f + e);
         loose = valid && (ub_thr < thr || P.first_pass == 2);
         if (valid) thr = fminf(thr, ub_thr);
     }
+    __syncthreads();
     if (P.bound_out && valid && !P.first_pass) P.bound_out[qid] = fminf(thr * thr, 3.402823466e+38f);
     if (P.first_pass) {
         // ---- the pages the loose queries scan first: of the nearest super-group of each, its two nearest pages ----
-        const int n_words = (I.n_supers + 31) / 32;
         __syncthreads();
         for (int w = t; w < n_words; w += kSelQ) near_map[w] = 0u;
         __syncthreads();
@@ -247,14 +259,16 @@ __global__ void __launch_bounds__(kSelQ) k_select_pages(const SelectParams P) {
     } else
     for (int g0 = 0; g0 < I.n_supers; g0 += kSelGroups) {
         const int ng = min(kSelGroups, I.n_supers - g0);
+        const unsigned int cand_w = near_map[g0 >> 5];  // block-uniform (written before the barrier above)
+        if (cand_w == 0u) continue;
         __syncthreads();  // previous round's readers of cs are done
         stage(I.scen, I.srad, I.scnt, g0, ng);
         __syncthreads();
         unsigned int gm = 0;
         if (valid)
             for (int gi = 0; gi < ng; gi++)
-                if (needs(cs + (size_t)gi * DS, rs[gi])) gm |= 1u << gi;
-        tests += valid ? (unsigned long long)ng : 0ull;
+                if (((cand_w >> gi) & 1u) && needs(cs + (size_t)gi * DS, rs[gi])) gm |= 1u << gi;
+        tests += valid ? (unsigned long long)__popc(cand_w) : 0ull;
         const unsigned int wm = __reduce_or_sync(0xffffffffu, gm);
         if (lane == 0 && wm) atomicOr(&s_mask, wm);
         __syncthreads();
