@@ -160,6 +160,28 @@ def cpu_reference_sample(data, queries, K, pct, n_sample, cores, host_tree=None)
     return dict(qps=n_sample / dt, kind="port", scanned_per_query=int(cnt[0]) / n_sample, cores=cores, idx=idx, dist2=d2)
 
 
+def dropin_e2e(data, queries, K, pct, reps=4):
+    """Convex_Tree<float>::kNN() of the drop-in subclass, timed inside the C++ harness (last of `reps` calls): pageable host
+    memory in and out, one GPU.  Also checks the harness's answers against nothing here -- tests/test_host_cpp.py does that."""
+    import re
+    import oracle as orc
+    from io_formats import write_fmat
+    binary = os.path.join(os.path.dirname(orc.REF_BIN), "ref_b200_knn")
+    if not os.access(binary, os.X_OK):
+        raise RuntimeError("oracle/_ref/ref_b200_knn not built")
+    with tempfile.TemporaryDirectory() as td:
+        dp, qp, op = os.path.join(td, "d.fmat"), os.path.join(td, "q.fmat"), os.path.join(td, "o.knn")
+        write_fmat(dp, data)
+        write_fmat(qp, queries)
+        r = subprocess.run([binary, dp, repr(float(pct)), "1", qp, str(K), "0", op, "0", "0", str(reps)], capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            raise RuntimeError("ref_b200_knn failed: " + r.stderr[-300:])
+        m = re.search(r"call_ms=([0-9.]+)", r.stderr)
+        ms = float(m.group(1))
+    return {"value": len(queries) / (ms / 1e3), "unit": "queries/s", "ms_per_call": ms,
+            "path": "Convex_Tree<float>::kNN() on B200_Convex_Tree (reference host tree, pageable Matrix<T> in, std::vector out), call %d of %d" % (reps, reps)}
+
+
 def parity(gpu_idx, gpu_d2, cpu):
     """bit-for-bit comparison of the GPU's answers with the CPU leg's on the same queries"""
     m = len(cpu["idx"])
@@ -333,6 +355,13 @@ def main():
                 exit_code = 1
         except Exception as ex:  # never lose the GPU line because the CPU leg failed
             line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": cores, "kind": "port", "sample": "failed: %r" % (ex,)}
+    # end to end through the C++ drop-in (integration/B200_Convex_Tree.h inside the reference's own headers, oracle/_ref/ref_b200_knn):
+    # the reference's constructor builds the tree on the host, kNN() takes the reference's pageable Matrix<T> and fills std::vectors
+    if world == 1 and not args.no_cpu_baseline and n * dim <= 32_000_000:
+        try:
+            line["e2e_dropin"] = dropin_e2e(data, queries, K, pct)
+        except Exception as ex:
+            line["e2e_dropin"] = {"skipped": repr(ex)}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
