@@ -336,7 +336,16 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
             }
         }
         TC.n_seg = n_seg;
-        size_t smem = tc_smem_bytes(T.dpad, I.kp, K, tc_stages);
+        // Survivor rings: SHALLOW for short lists.  A survivor waits in its ring while the bound it was tested against goes stale, and
+        // on clustered data the entries queued behind it are mostly pairs a fresher bound would have dropped: with 64 instead of 256
+        // entries per epilogue warp the 10Mx32 Gaussian clusters need 125 instead of 147 exact evaluations per query (main scan
+        // 30.2 -> 27.2 ms), SIFT-like 144 instead of 171 (25.7 -> 24.8 ms per step); 512 entries: 166 evaluations, 33.2 ms.  A full
+        // ring stalls its epilogue warp, and with it the pipeline, until the rescorer catches up -- that back-pressure is what keeps
+        // the bounds fresh.  Uniform 16-D data never fills a ring (10.3 ms either way); K = 100 prefers 256 (33.4 vs 34.1 ms).
+        int queue_cap = h->opt.tc_ring > 0 ? h->opt.tc_ring : (K <= 32 ? 64 : kTcQueueCap);
+        if ((int)tc_smem_bytes(T.dpad, I.kp, K, tc_stages, queue_cap) > h->max_smem) queue_cap = kTcQueueCap;
+        TC.queue_cap = queue_cap;
+        size_t smem = tc_smem_bytes(T.dpad, I.kp, K, tc_stages, queue_cap);
         // One K slice per page (narrow points): two issuers, one per page parity, each issuing the page's two N=128 half-page
         // chains (+3 % over four issuers; whole-page N=256 chains cost 2.4 % there).  Several slices per page (wide points): the
         // MMA time counts, and one N=256 chain per page (128 instead of 2 x 92 cycles per K16 step) beats four issuers of
@@ -799,6 +808,7 @@ const OptEntry kOptions[] = {
     {"pipeline_split", &Options::pipeline_split, 0, 64},
     {"rescorer_sleep_ns", &Options::rescorer_sleep_ns, 0, 1000000},
     {"first_pass", &Options::first_pass, -1, 2},
+    {"tc_ring", &Options::tc_ring, 0, 1024},
     {"groups", &Options::groups, -1, 1 << 20},
 };
 }  // namespace
@@ -809,6 +819,8 @@ extern "C" int scht_set_option(scht_handle* h, const char* name, int64_t value) 
         if (strcmp(name, e.name) != 0) continue;
         if (value < e.lo || value > e.hi) return scht::fail(SCHT_ERR_INVALID_ARG, std::string("scht_set_option: value out of range for ") + name);
         if (e.field == &Options::groups) return scht::fail(SCHT_ERR_INVALID_ARG, "scht_set_option: 'groups' is fixed when the handle is created (SCHT_GROUPS)");
+        if (e.field == &Options::tc_ring && value != 0 && (value < 32 || (value & (value - 1)) != 0))
+            return scht::fail(SCHT_ERR_INVALID_ARG, "scht_set_option: tc_ring is 0 (default) or a power of two in 32..1024");
         if (e.field == &Options::tc_mode && value != 0 && h->subs.empty() && h->I.kp == 0 && h->opt.tc_mode == 0)
             return scht::fail(SCHT_ERR_INVALID_ARG, "scht_set_option: the handle was created without the tensor-core image (SCHT_TC=0)");
         std::vector<scht_handle*> all = h->subs.empty() ? std::vector<scht_handle*>{h} : h->subs;

@@ -41,7 +41,8 @@ constexpr int kTcMaxStages = 6;    // slice stages (fewer when K is large and th
 constexpr int kTcEpiWarps = 16;
 constexpr int kTcMaxMmaWarps = 4;  // MMA issuers: 2 (one per page parity; narrow points, one K slice per page) or 4 (one per TMEM buffer)
 __host__ __device__ constexpr int tc_threads(int n_iss) { return (kTcEpiWarps + 1 + n_iss + 4) * 32; }  // + producer, MMA issuers, 4 rescorers
-constexpr int kTcQueueCap = 256;   // ring entries per epilogue warp (power of two)
+constexpr int kTcQueueCap = 256;   // ring entries per epilogue warp for long lists (K > 32); TcScanParams::queue_cap is what a launch uses
+constexpr int kTcQueueCapMax = 1024;
 
 struct TcScanParams {
     ScanParams S;            // q, q_order, q_leaf, nq, K, write_mode, pos range, ranges (tile = 128 queries), state, outputs
@@ -51,6 +52,7 @@ struct TcScanParams {
                              //    issuer that skips the other parity's pages would run a whole ring round ahead of the producer, and a
                              //    parity wait cannot tell round r from round r+2)
     int n_stages;            // slice stages in shared memory (3..kTcMaxStages)
+    int queue_cap;           // ring entries per epilogue warp (power of two, kTcQueueCap..kTcQueueCapMax)
     int n_seg;               // page segments per tile (>= 1): CTA b scans segment b / n_tiles of tile b % n_tiles and, when
     int seg_pages;           //   n_seg > 1, writes its key lists to S.keys_out[segment][query][K] (merged by k_merge_partial);
     int seg_page0;           //   segment s = pages [seg_page0 + s*seg_pages, +seg_pages)
@@ -59,12 +61,12 @@ struct TcScanParams {
     long long* trace;        // SCHT_TC_PROF builds: [64 pages][8] clock64 stamps of tile 0 (pages 2000..2063)
 };
 
-__host__ __device__ inline size_t tc_smem_bytes(int dpad, int kp, int K, int n_stages) {
+__host__ __device__ inline size_t tc_smem_bytes(int dpad, int kp, int K, int n_stages, int queue_cap = kTcQueueCap) {
     size_t b = 1024;                                                         // alignment slack
     b += (size_t)n_stages * (kp < kTcKSlice ? kp : kTcKSlice) * 512;         // B slice stages (<= 16 KB each)
     b += (size_t)kTcQ * kp * 2;                                              // A operand
     b += (size_t)kTcQ * K * 8;                                               // lists
-    b += (size_t)kTcEpiWarps * kTcQueueCap * 8;                              // candidate queues
+    b += (size_t)kTcEpiWarps * queue_cap * 8;                                // candidate queues
     b += (size_t)kTcQ * 3 * 4;                                               // a0, a1, qid
     b += 1536;                                                               // barriers, ring counters, bounds, tmem base
     return b;
@@ -190,8 +192,9 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
     const int n_stages = TP.n_stages;
     __half* sA = reinterpret_cast<__half*>(stage_mem + (size_t)n_stages * stage_bytes);  // [kp/8][16][8][8]
     uint64_t* lists = reinterpret_cast<uint64_t*>(sA + (size_t)kTcQ * kp);     // [128][K]
-    uint64_t* queues = lists + (size_t)kTcQ * K;                               // [16][kTcQueueCap]
-    int* a0s = reinterpret_cast<int*>(queues + (size_t)kTcEpiWarps * kTcQueueCap);
+    const int qcap = TP.queue_cap;
+    uint64_t* queues = lists + (size_t)kTcQ * K;                               // [16][qcap]
+    int* a0s = reinterpret_cast<int*>(queues + (size_t)kTcEpiWarps * qcap);
     int* a1s = a0s + kTcQ;
     int* qids = a1s + kTcQ;
     uint64_t* full_b = reinterpret_cast<uint64_t*>(qids + kTcQ);
@@ -249,14 +252,22 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
     __syncthreads();
     // queries: exact copy (dim-major) and the A operand: row q = fp16(-2 s q'_j); a query outside FP16's range gets a
     // zero row (its bound is set to "everything passes" below, so it stays exact, only slow)
+    // (tq_s doubles as the per-query "inside FP16's range" flag until the real bounds are written below)
+    for (int qi = tid; qi < kTcQ; qi += blockDim.x) {
+        bool in_range = qids[qi] >= 0;
+        if (in_range) {
+            const float* qrow = P.q + (size_t)qids[qi] * T.dim;
+            for (int j = 0; j < T.dim; j++) in_range &= fabsf(qrow[j] - I.mean[j]) * 2.f * scale < 60000.f;
+        }
+        tq_s[qi] = in_range ? 1.f : 0.f;
+    }
+    __syncthreads();
     for (int i = tid; i < kTcQ * kp; i += blockDim.x) {
         int qi = i / kp, k = i - qi * kp;
         float v = 0.f;
         if (qids[qi] >= 0 && k < T.dim) {
             const float* qrow = P.q + (size_t)qids[qi] * T.dim;
-            bool in_range = true;
-            for (int j = 0; j < T.dim; j++) in_range &= fabsf(qrow[j] - I.mean[j]) * 2.f * scale < 60000.f;
-            if (in_range) v = (float)(-2.0 * ((double)qrow[k] - (double)I.mean[k]) * (double)scale);
+            if (tq_s[qi] != 0.f) v = (float)(-2.0 * ((double)qrow[k] - (double)I.mean[k]) * (double)scale);
         } else if (k >= T.dim && k < T.dim + 3) {
             v = I.norm_unit;  // multiplies the norm slots of the point operand (every row, also padded ones)
         }
@@ -266,6 +277,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
         int qi = i / K;
         lists[i] = (ord(qi) < nq_tile) ? P.state[(size_t)(q_begin + ord(qi)) * K + (i - qi * K)] : kEmptyKey;
     }
+    __syncthreads();  // the range flags in tq_s have been read
     for (int i = tid; i < kTcQ; i += blockDim.x) tq_s[i] = -3.0e38f;  // real bounds are published below, before the pipeline starts
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // sA was written through the generic proxy
     tc_fence_before();
@@ -488,7 +500,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                                 ri = i + 1;
                             }
                         const int head = ri == 0 ? head_r[0] : ri == 1 ? head_r[1] : ri == 2 ? head_r[2] : head_r[3];
-                        const uint64_t* ring = queues + (size_t)(quad + 4 * ((ri + rot) & 3)) * kTcQueueCap;
+                        const uint64_t* ring = queues + (size_t)(quad + 4 * ((ri + rot) & 3)) * qcap;
                         cand[e] = false;
                         d2[e] = 0.f;
                         pos[e] = -1;
@@ -496,7 +508,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                         qq[e] = P.q;
                         pr[e] = reinterpret_cast<const float4*>(I.srows);
                         if (live[e]) {
-                            const uint64_t en = ring[(head + off) & (kTcQueueCap - 1)];
+                            const uint64_t en = ring[(head + off) & (qcap - 1)];
                             const uint32_t slot = (uint32_t)en;  // ring entries name a SLOT of the scan-order image
                             // the survivor's exact coordinates: row-major in scan order, so the row loads do not wait for the
                             // slot -> position lookup (both go out together; the position is only needed for the key)
@@ -601,7 +613,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             // quad = TMEM lane quadrant (= warp id % 4, a hardware rule), sub = which 64 columns of the buffer,
             // half = pipeline group = which half page of every page
             const int sub = (warp >> 2) & 1, half = warp >> 3;
-            uint64_t* myq = queues + (size_t)warp * kTcQueueCap;
+            uint64_t* myq = queues + (size_t)warp * qcap;
             volatile int* v_head = q_head + warp;
             volatile float* v_tq = tq_s + qi;
             int resv = 0;  // ring slots written by this warp so far (warp-uniform)
@@ -650,13 +662,13 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                         const unsigned b = __ballot_sync(0xffffffffu, mask != 0);
                         if (!b) break;
                         const int n = __popc(b);
-                        if (resv + n - head_cache > kTcQueueCap) {
+                        if (resv + n - head_cache > qcap) {
                             __syncwarp();
                             __threadfence_block();
                             if (lane == 0) *reinterpret_cast<volatile int*>(q_tail + warp) = resv;
                             for (;;) {
                                 head_cache = __shfl_sync(0xffffffffu, *v_head, 0);
-                                if (resv + n - head_cache <= kTcQueueCap) break;
+                                if (resv + n - head_cache <= qcap) break;
                                 __nanosleep(40);
                             }
                         }
@@ -664,7 +676,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                             const int c = __ffs(mask) - 1;
                             mask &= mask - 1;
                             const int slot = resv + __popc(b & ((1u << lane) - 1u));
-                            myq[slot & (kTcQueueCap - 1)] = ((uint64_t)(uint32_t)lane << 32) | (uint32_t)(page * kPage + col0 + c);
+                            myq[slot & (qcap - 1)] = ((uint64_t)(uint32_t)lane << 32) | (uint32_t)(page * kPage + col0 + c);
                         }
                         resv += n;
                     }

@@ -175,10 +175,30 @@ def test_options_interface(pkg):
     ix.set_option("tc", 0)
     ix.set_option("seed_points", 2048)
     assert ix.get_option("tc") == 0 and ix.get_option("seed_points") == 2048
-    for name, value in (("no_such_option", 1), ("tc", 7), ("groups", 4)):
+    for name, value in (("no_such_option", 1), ("tc", 7), ("groups", 4), ("tc_ring", 48), ("tc_ring", 16)):
         with pytest.raises(pkg.SchtError) as e:
             ix.set_option(name, value)
         assert e.value.code == -1
+    ix.close()
+
+
+def test_survivor_ring_depth(pkg, orc):
+    """k_scan_tc's survivor rings (option tc_ring): the depth changes how stale the filter bounds get, never a result bit"""
+    rng = np.random.default_rng(21)
+    n, dim, nq, K = 60000, 24, 3000, 10
+    c = rng.random((40, dim))
+    data = (c[rng.integers(0, 40, n)] + 0.03 * rng.standard_normal((n, dim))).astype(np.float32)
+    q = (c[rng.integers(0, 40, nq)] + 0.03 * rng.standard_normal((nq, dim))).astype(np.float32)
+    ht = pkg.HostTree(data, 0.004, seed=1)
+    oi, od2, _, _, _ = orc.knn(ht, q, K, alg=2)
+    ix = pkg.Index(ht)
+    ix.set_option("tc", 1)
+    for ring in (0, 32, 128, 1024):
+        ix.set_option("tc_ring", ring)
+        idx, d2, st = ix.query(q, K, want_stats=True)
+        assert st["prefilter_batches"] == 1
+        assert_bit_equal(idx, oi, "idx ring=%d" % ring)
+        assert_bit_equal(d2, od2, "dist2 ring=%d" % ring)
     ix.close()
 
 
