@@ -345,6 +345,7 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
         int queue_cap = h->opt.tc_ring > 0 ? h->opt.tc_ring : (K <= 32 ? 64 : kTcQueueCap);
         if ((int)tc_smem_bytes(T.dpad, I.kp, K, tc_stages, queue_cap) > h->max_smem) queue_cap = kTcQueueCap;
         TC.queue_cap = queue_cap;
+        TC.recheck = (h->opt.tc_recheck && (long long)I.n_slots <= (1ll << kTcSlotBits)) ? 1 : 0;
         size_t smem = tc_smem_bytes(T.dpad, I.kp, K, tc_stages, queue_cap);
         // One K slice per page (narrow points): two issuers, one per page parity, each issuing the page's two N=128 half-page
         // chains (+3 % over four issuers; whole-page N=256 chains cost 2.4 % there).  Several slices per page (wide points): the
@@ -809,6 +810,7 @@ const OptEntry kOptions[] = {
     {"rescorer_sleep_ns", &Options::rescorer_sleep_ns, 0, 1000000},
     {"first_pass", &Options::first_pass, -1, 2},
     {"tc_ring", &Options::tc_ring, 0, 1024},
+    {"tc_recheck", &Options::tc_recheck, 0, 1},
     {"groups", &Options::groups, -1, 1 << 20},
 };
 }  // namespace

@@ -43,6 +43,9 @@ constexpr int kTcMaxMmaWarps = 4;  // MMA issuers: 2 (one per page parity; narro
 __host__ __device__ constexpr int tc_threads(int n_iss) { return (kTcEpiWarps + 1 + n_iss + 4) * 32; }  // + producer, MMA issuers, 4 rescorers
 constexpr int kTcQueueCap = 256;   // ring entries per epilogue warp for long lists (K > 32); TcScanParams::queue_cap is what a launch uses
 constexpr int kTcQueueCapMax = 1024;
+constexpr int kTcTake = 4;         // wide points: ring entries a rescorer lane takes per round (re-checked against the current bound first)
+constexpr int kTcPassCap = 32 * kTcTake;
+constexpr int kTcSlotBits = 27;    // ring entries that carry the prefilter value name the slot in 27 bits (and the lane in 5)
 
 struct TcScanParams {
     ScanParams S;            // q, q_order, q_leaf, nq, K, write_mode, pos range, ranges (tile = 128 queries), state, outputs
@@ -53,6 +56,8 @@ struct TcScanParams {
                              //    parity wait cannot tell round r from round r+2)
     int n_stages;            // slice stages in shared memory (3..kTcMaxStages)
     int queue_cap;           // ring entries per epilogue warp (power of two, kTcQueueCap..kTcQueueCapMax)
+    int recheck;             // wide points: ring entries carry the pair's prefilter value and the rescorer drops an entry that the query's
+                             //   bound has overtaken while it waited (needs n_slots <= 2^27)
     int n_seg;               // page segments per tile (>= 1): CTA b scans segment b / n_tiles of tile b % n_tiles and, when
     int seg_pages;           //   n_seg > 1, writes its key lists to S.keys_out[segment][query][K] (merged by k_merge_partial);
     int seg_page0;           //   segment s = pages [seg_page0 + s*seg_pages, +seg_pages)
@@ -67,6 +72,7 @@ __host__ __device__ inline size_t tc_smem_bytes(int dpad, int kp, int K, int n_s
     b += (size_t)kTcQ * kp * 2;                                              // A operand
     b += (size_t)kTcQ * K * 8;                                               // lists
     b += (size_t)kTcEpiWarps * queue_cap * 8;                                // candidate queues
+    b += (size_t)4 * kTcPassCap * 8;                                         // rescorers: the entries of a round that passed the re-check
     b += (size_t)kTcQ * 3 * 4;                                               // a0, a1, qid
     b += 1536;                                                               // barriers, ring counters, bounds, tmem base
     return b;
@@ -169,6 +175,20 @@ __device__ __forceinline__ float fmin2f(float a, float b) {
     asm("min.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
     return d;
 }
+// v[c] for a run-time c without indexing the register array (which would move it to local memory): 31 selects
+__device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int c) {
+    const bool b0 = c & 1, b1 = c & 2, b2 = c & 4;
+    uint32_t g[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t y0 = b0 ? v[8 * i + 1] : v[8 * i], y1 = b0 ? v[8 * i + 3] : v[8 * i + 2];
+        const uint32_t y2 = b0 ? v[8 * i + 5] : v[8 * i + 4], y3 = b0 ? v[8 * i + 7] : v[8 * i + 6];
+        const uint32_t z0 = b1 ? y1 : y0, z1 = b1 ? y3 : y2;
+        g[i] = b2 ? z1 : z0;
+    }
+    const uint32_t h0 = (c & 8) ? g[1] : g[0], h1 = (c & 8) ? g[3] : g[2];
+    return (c & 16) ? h1 : h0;
+}
 // N_ISS = MMA issuer warps: 2 (23 warps: 80 registers per thread, the min trees keep their values in registers) or 4 (25 warps, 72)
 // ROWS = wide points (more than one 16-dimension slice): the rescorers take two ring entries per lane and round instead of one
 // (a compile-time choice because the pipeline is sensitive to the kernel's code size and register count: +2 % on 16-dimensional points)
@@ -194,7 +214,8 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
     uint64_t* lists = reinterpret_cast<uint64_t*>(sA + (size_t)kTcQ * kp);     // [128][K]
     const int qcap = TP.queue_cap;
     uint64_t* queues = lists + (size_t)kTcQ * K;                               // [16][qcap]
-    int* a0s = reinterpret_cast<int*>(queues + (size_t)kTcEpiWarps * qcap);
+    uint64_t* passed = queues + (size_t)kTcEpiWarps * qcap;                    // [4][kTcPassCap]
+    int* a0s = reinterpret_cast<int*>(passed + (size_t)4 * kTcPassCap);
     int* a1s = a0s + kTcQ;
     int* qids = a1s + kTcQ;
     uint64_t* full_b = reinterpret_cast<uint64_t*>(qids + kTcQ);
@@ -458,6 +479,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                 // Fair when the rings are busy (large K): every ring gets 16 of the 64 places first, the rest goes to whoever has
                 // more, starting at a ring that rotates from round to round (a starved ring stalls its epilogue warp, hence the MMA).
                 constexpr int kE = ROWS ? 2 : 1;  // (narrow points, i.e. the uniform 16-D benchmark, have ~20 survivors per query: one entry per lane, 2 % faster there)
+                constexpr int kTake = ROWS ? kTcTake : 1;  // ring entries per lane and round
                 bool all_done = true;
                 int head_r[4], n_r[4], avail_r[4], total = 0;
 #pragma unroll
@@ -468,12 +490,12 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                     head_r[i] = v_head[w];
                     avail_r[i] = tail - head_r[i];
                     all_done &= (done != 0) && (avail_r[i] == 0);
-                    n_r[i] = min(avail_r[i], 8 * kE);
+                    n_r[i] = min(avail_r[i], 8 * kTake);
                     total += n_r[i];
                 }
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int extra = min(avail_r[i] - n_r[i], 32 * kE - total);
+                    const int extra = min(avail_r[i] - n_r[i], 32 * kTake - total);
                     n_r[i] += extra;
                     total += extra;
                 }
@@ -482,6 +504,123 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                     __nanosleep((unsigned)TP.rescorer_sleep_ns);  // survivors are rare on uniform data (~1 per 10 pages and warp): poll seldom, the pipeline warps need the issue slots
                     continue;
                 }
+                if constexpr (ROWS) {
+                    // ---- wide points: take up to 4 entries per lane, keep what the queries' CURRENT bounds still admit, evaluate ----
+                    // A survivor waits in its ring while its query's bound tightens; on clustered data a third of the entries are
+                    // stale by the time they are taken (147 evaluations per query with 256-entry rings against 120 with 32-entry
+                    // ones).  With `recheck` an entry carries the pair's prefilter value, so the rescorer repeats the epilogue's
+                    // test with the bound of NOW -- one shared-memory read -- before it spends a row fetch and an FP64 chain on it.
+                    // What is left is compacted through shared memory, so the evaluation rounds below are full.
+                    __threadfence_block();  // entries below a `tail` were written before it was published
+                    const bool recheck = TP.recheck != 0;
+                    uint64_t* mine = passed + (size_t)quad * kTcPassCap;
+                    int n_pass = 0;
+#pragma unroll
+                    for (int e = 0; e < kTake; e++) {
+                        int ri = 0, off = lane + 32 * e;
+                        bool ok = off < total;
+#pragma unroll
+                        for (int i = 0; i < 3; i++)
+                            if (ri == i && off >= n_r[i]) {
+                                off -= n_r[i];
+                                ri = i + 1;
+                            }
+                        const int head = ri == 0 ? head_r[0] : ri == 1 ? head_r[1] : ri == 2 ? head_r[2] : head_r[3];
+                        const uint64_t* ring = queues + (size_t)(quad + 4 * ((ri + rot) & 3)) * qcap;
+                        uint64_t en = 0;
+                        if (ok) {
+                            en = ring[(head + off) & (qcap - 1)];
+                            if (recheck) {
+                                const uint32_t lq = ((uint32_t)en >> kTcSlotBits) & 31u;
+                                ok = __uint_as_float((uint32_t)(en >> 32)) <= v_tq[quad * 32 + lq];
+                                en = ((uint64_t)lq << 32) | ((uint32_t)en & ((1u << kTcSlotBits) - 1u));
+                            }
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, ok);
+                        if (ok) mine[n_pass + __popc(m & ((1u << lane) - 1u))] = en;
+                        n_pass += __popc(m);
+                    }
+                    __syncwarp();
+                    if (lane < 4) {  // the ring slots may be reused
+                        const int nh = lane == 0 ? head_r[0] + n_r[0] : lane == 1 ? head_r[1] + n_r[1] : lane == 2 ? head_r[2] + n_r[2] : head_r[3] + n_r[3];
+                        v_head[quad + 4 * ((lane + rot) & 3)] = nh;
+                    }
+                    rot++;
+                    __syncwarp();  // ... and every lane reads the new heads in the next round; `mine` is complete
+                    for (int c0 = 0; c0 < n_pass; c0 += 32 * kE) {
+                        bool live[kE], cand[kE];
+                        float d2[kE];
+                        int pos[kE], cq[kE];
+                        const float* qq[kE];
+                        const float4* pr[kE];
+#pragma unroll
+                        for (int e = 0; e < kE; e++) {
+                            const int x = c0 + lane + 32 * e;
+                            live[e] = x < n_pass;
+                            cand[e] = false;
+                            d2[e] = 0.f;
+                            pos[e] = -1;
+                            cq[e] = 0;
+                            qq[e] = P.q;
+                            pr[e] = reinterpret_cast<const float4*>(I.srows);
+                            if (live[e]) {
+                                const uint64_t en = mine[x];
+                                const uint32_t slot = (uint32_t)en;  // a SLOT of the scan-order image
+                                // the survivor's exact coordinates: row-major in scan order, so the row loads do not wait for the
+                                // slot -> position lookup (both go out together; the position is only needed for the key)
+                                pr[e] = reinterpret_cast<const float4*>(I.srows + (size_t)slot * dpad);
+                                prefetch_row(pr[e], dpad);
+                                pos[e] = I.slot_pos[slot];  // -1: padding
+                                cq[e] = (int)(en >> 32);
+                                qq[e] = P.q + (size_t)qids[quad * 32 + cq[e]] * T.dim;  // the query's original coordinates
+                                n_exact++;
+                            }
+                        }
+                        // loads first (8 dims of every entry), then the sequential reference chains side by side
+                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                            float pv[kE][8], qv[kE][8];
+#pragma unroll
+                            for (int e = 0; e < kE; e++) {
+                                const float4 x = live[e] ? __ldg(pr[e] + (j0 >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 y = (live[e] && j0 + 4 < dpad) ? __ldg(pr[e] + (j0 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                pv[e][0] = x.x, pv[e][1] = x.y, pv[e][2] = x.z, pv[e][3] = x.w;
+                                pv[e][4] = y.x, pv[e][5] = y.y, pv[e][6] = y.z, pv[e][7] = y.w;
+#pragma unroll
+                                for (int u = 0; u < 8; u++) qv[e][u] = (j0 + u < T.dim) ? qq[e][j0 + u] : 0.f;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (j0 + u < T.dim) {
+#pragma unroll
+                                    for (int e = 0; e < kE; e++) d2[e] = ref_acc_sq(d2[e], pv[e][u] - qv[e][u]);
+                                }
+                        }
+#pragma unroll
+                        for (int e = 0; e < kE; e++) {
+                            cand[e] = live[e] && pos[e] >= 0 && (d2[e] < 3.402823466e+38f) && (pos[e] >= P.pos_lo) && (pos[e] < P.pos_hi);
+                            if (cand[e]) cand[e] = ((uint64_t)__float_as_uint(d2[e]) << 32) <= lists[(size_t)(quad * 32 + cq[e]) * K + K - 1];
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int e = 0; e < kE; e++) {
+                            unsigned m = __ballot_sync(0xffffffffu, cand[e]);
+                            while (m) {
+                                int src = __ffs(m) - 1;
+                                m &= m - 1;
+                                float cd2 = __shfl_sync(0xffffffffu, d2[e], src);
+                                int cpos = __shfl_sync(0xffffffffu, pos[e], src);
+                                int ccq = __shfl_sync(0xffffffffu, cq[e], src);
+                                const int a0 = a0s[quad * 32 + ccq], a1 = a1s[quad * 32 + ccq];
+                                uint32_t low = TP.brute ? (uint32_t)T.orig_idx[cpos] : (((cpos >= a0 && cpos < a1) ? 0u : 0x80000000u) | (uint32_t)cpos);
+                                uint64_t key = ((uint64_t)__float_as_uint(cd2) << 32) | low;
+                                uint64_t* L = lists + (size_t)(quad * 32 + ccq) * K;
+                                if (key < L[K - 1]) n_ins += list_insert(L, K, key, lane);
+                            }
+                        }
+                        // publish the (possibly) tightened bound of this lane's query
+                        v_tq[qi] = bound_of(__uint_as_float((uint32_t)(lists[(size_t)qi * K + K - 1] >> 32)));
+                    }
+                } else
                 {
                     __threadfence_block();  // entries below a `tail` were written before it was published
                     bool live[kE], cand[kE];
@@ -672,7 +811,15 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                                 __nanosleep(40);
                             }
                         }
-                        if (mask) {
+                        if (ROWS && TP.recheck) {  // (warp-uniform) the entry carries the pair's prefilter value
+                            const int c = mask ? __ffs(mask) - 1 : 0;
+                            const uint32_t val = select32(v, c);
+                            if (mask) {
+                                mask &= mask - 1;
+                                const int slot = resv + __popc(b & ((1u << lane) - 1u));
+                                myq[slot & (qcap - 1)] = ((uint64_t)val << 32) | ((uint32_t)lane << kTcSlotBits) | (uint32_t)(page * kPage + col0 + c);
+                            }
+                        } else if (mask) {
                             const int c = __ffs(mask) - 1;
                             mask &= mask - 1;
                             const int slot = resv + __popc(b & ((1u << lane) - 1u));
