@@ -183,7 +183,8 @@ def test_options_interface(pkg):
 
 
 def test_survivor_ring_depth(pkg, orc):
-    """k_scan_tc's survivor rings (option tc_ring): the depth changes how stale the filter bounds get, never a result bit"""
+    """k_scan_tc's survivor rings (options tc_ring, tc_recheck): depth and re-check change how many stale survivors reach
+    the exact evaluation, never a result bit"""
     rng = np.random.default_rng(21)
     n, dim, nq, K = 60000, 24, 3000, 10
     c = rng.random((40, dim))
@@ -193,12 +194,16 @@ def test_survivor_ring_depth(pkg, orc):
     oi, od2, _, _, _ = orc.knn(ht, q, K, alg=2)
     ix = pkg.Index(ht)
     ix.set_option("tc", 1)
-    for ring in (0, 32, 128, 1024):
+    evals = {}
+    for ring, recheck in ((0, 1), (32, 1), (128, 0), (1024, 1), (1024, 0)):
         ix.set_option("tc_ring", ring)
+        ix.set_option("tc_recheck", recheck)  # entries carry the prefilter value; stale ones are dropped before the exact evaluation
         idx, d2, st = ix.query(q, K, want_stats=True)
         assert st["prefilter_batches"] == 1
-        assert_bit_equal(idx, oi, "idx ring=%d" % ring)
-        assert_bit_equal(d2, od2, "dist2 ring=%d" % ring)
+        assert_bit_equal(idx, oi, "idx ring=%d recheck=%d" % (ring, recheck))
+        assert_bit_equal(d2, od2, "dist2 ring=%d recheck=%d" % (ring, recheck))
+        evals[(ring, recheck)] = st["exact_reevaluations"]
+    assert evals[(1024, 1)] <= evals[(1024, 0)]
     ix.close()
 
 
