@@ -310,6 +310,7 @@ int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
         TC.brute = brute ? 1 : 0;
         TC.n_stages = tc_stages;
         TC.rescorer_sleep_ns = h->opt.rescorer_sleep_ns;
+        TC.ring_wait_ns = h->opt.ring_wait_ns;
         // Tail effect: n_tiles CTAs of equal length on n_sm SMs take ceil(n_tiles/n_sm) rounds (782 tiles on 148 SMs: 6 rounds
         // for 5.28 rounds of work).  Splitting every tile's page list into S segments (own CTA each, partial lists merged by
         // k_merge_partial) makes the rounds S times shorter: pick the S <= 8 with the smallest ceil(S*n_tiles/n_sm)/S, charging
@@ -811,6 +812,7 @@ const OptEntry kOptions[] = {
     {"first_pass", &Options::first_pass, -1, 2},
     {"tc_ring", &Options::tc_ring, 0, 1024},
     {"tc_recheck", &Options::tc_recheck, 0, 1},
+    {"ring_wait_ns", &Options::ring_wait_ns, 0, 1000000},
     {"groups", &Options::groups, -1, 1 << 20},
 };
 }  // namespace

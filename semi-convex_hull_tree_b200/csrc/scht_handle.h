@@ -85,6 +85,7 @@ struct Options {
     int rescorer_sleep_ns = SCHT_RESCORER_SLEEP_NS_DEFAULT;  // k_scan_tc: an idle rescorer warp's pause between polls (1500 and 8000 measured equal on uniform data)
     int first_pass = -1;        // pruned prefilter batches: 0 = bound test only, 1 = queries with a loose seed bound scan their nearest pages first, 2 = all queries do, -1 = auto
     int tc_ring = 0;            // k_scan_tc: survivor ring entries per epilogue warp: 0 auto (64 for K <= 32, else 256) or a power of two in 32..1024
+    int ring_wait_ns = 1000;    // k_scan_tc: pause of an epilogue warp between polls while its survivor ring is full (40 -> 1000 ns: K=100 main scan 33.6 -> 32.3 ms, its polls share an issue port with a rescorer)
     int tc_recheck = 1;         // k_scan_tc, wide points: ring entries carry the prefilter value, stale ones are dropped before the exact evaluation
     int pipeline_split = 0;     // split a single-batch scht_query call into this many sub-batches so that its copies overlap (0/1: off)
 };

@@ -62,6 +62,7 @@ struct TcScanParams {
     int seg_pages;           //   n_seg > 1, writes its key lists to S.keys_out[segment][query][K] (merged by k_merge_partial);
     int seg_page0;           //   segment s = pages [seg_page0 + s*seg_pages, +seg_pages)
     int rescorer_sleep_ns;   // an idle rescorer's pause between polls of its rings
+    int ring_wait_ns;        // an epilogue warp's pause between polls of its rescorer's head while its ring is full
     int debug;               // SCHT_TC_PROF builds only: 1 = no pair passes the filter, 2 = also skip the min tree
     long long* trace;        // SCHT_TC_PROF builds: [64 pages][8] clock64 stamps of tile 0 (pages 2000..2063)
 };
@@ -808,7 +809,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                             for (;;) {
                                 head_cache = __shfl_sync(0xffffffffu, *v_head, 0);
                                 if (resv + n - head_cache <= qcap) break;
-                                __nanosleep(40);
+                                __nanosleep((unsigned)TP.ring_wait_ns);
                             }
                         }
                         if (ROWS && TP.recheck) {  // (warp-uniform) the entry carries the pair's prefilter value
