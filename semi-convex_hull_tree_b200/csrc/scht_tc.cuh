@@ -758,7 +758,6 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             volatile float* v_tq = tq_s + qi;
             int resv = 0;  // ring slots written by this warp so far (warp-uniform)
             int head_cache = 0;  // last value of the rescorer's head this warp has seen (warp-uniform; only re-read when the ring looks full)
-            unsigned long long n_pairs = 0;
             asm volatile("bar.sync %0, 160;" ::"r"(1 + quad) : "memory");  // the rescorer has published the initial bounds
             float Tq = *v_tq;
 
@@ -856,7 +855,6 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
                 TC_STAMP(warp == 0, pg, 6);
                 process(va, col0 + 32);
                 TC_STAMP(warp == 0, pg, 7);
-                if (half == 0 && sub == 0) n_pairs += (unsigned long long)min(kPage, I.n_slots - page * kPage);
                 pg++;
             }
             __syncwarp();
@@ -864,7 +862,7 @@ __global__ void __launch_bounds__(tc_threads(N_ISS), 1) k_scan_tc(const TcScanPa
             if (lane == 0) *reinterpret_cast<volatile int*>(q_done + warp) = 1;
             if (P.counters && half == 0 && sub == 0 && lane == 0) {
                 int nvalid = max(0, min(32, (nq_tile - quad + 3) / 4));  // slots of the quadrant with ord(slot) < nq_tile
-                atomicAdd(&P.counters[0], n_pairs * (unsigned long long)nvalid);
+                atomicAdd(&P.counters[0], (unsigned long long)pg * kPage * (unsigned long long)nvalid);  // every scan page is 256 slots (padding included)
             }
         }
     }
