@@ -128,19 +128,38 @@ __global__ void k_descend(DevTree T, const float* __restrict__ q, int nq, int* _
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     const float* qi = q + (size_t)i * T.dim;
+    const bool vec4 = (T.dim & 3) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0;  // query rows 16-byte aligned (the centre rows always are)
     int node = 0, levels = 0;
     NodeRec nr = T.nodes[0];
     while (nr.leaf < 0) {
         const float* lc = T.node_lc + (size_t)node * T.dpad;
         const float* rc = T.node_rc + (size_t)node * T.dpad;
-        // Only the COMPARISON has to be the reference's.  A plain FP32 FMA chain is within (dim + 2) 2^-24 (relative) of the
-        // reference's value (same differences, same order, one rounding per step instead of the float(double) step), so when
-        // the two distances differ by more than 2^-14 of their sum the outcome is certain; near-ties take the exact arithmetic.
+        // Only the COMPARISON has to be the reference's.  A plain FP32 FMA evaluation (any summation order) is within
+        // (dim + 2) 2^-24 (relative) of the reference's value (same differences, one rounding per step instead of the
+        // float(double) step), so when the two distances differ by more than 2^-14 of their sum the outcome is certain;
+        // near-ties take the exact arithmetic.
         float l = 0.f, r = 0.f;
-        for (int j = 0; j < T.dim; j++) {
-            const float x = qi[j], dl = x - lc[j], dr = x - rc[j];
-            l = fmaf(dl, dl, l);
-            r = fmaf(dr, dr, r);
+        if (vec4) {  // 16-byte loads, two independent chains per side: the level's latency is what this kernel pays
+            float l1 = 0.f, r1 = 0.f;
+            const float4* q4 = reinterpret_cast<const float4*>(qi);
+            const float4* lc4 = reinterpret_cast<const float4*>(lc);
+            const float4* rc4 = reinterpret_cast<const float4*>(rc);
+#pragma unroll 4
+            for (int j = 0; j < (T.dim >> 2); j++) {
+                const float4 x = __ldg(q4 + j), a = __ldg(lc4 + j), b = __ldg(rc4 + j);
+                const float a0 = x.x - a.x, a1 = x.y - a.y, a2 = x.z - a.z, a3 = x.w - a.w;
+                const float b0 = x.x - b.x, b1 = x.y - b.y, b2 = x.z - b.z, b3 = x.w - b.w;
+                l = fmaf(a0, a0, l), l1 = fmaf(a1, a1, l1), l = fmaf(a2, a2, l), l1 = fmaf(a3, a3, l1);
+                r = fmaf(b0, b0, r), r1 = fmaf(b1, b1, r1), r = fmaf(b2, b2, r), r1 = fmaf(b3, b3, r1);
+            }
+            l += l1;
+            r += r1;
+        } else {
+            for (int j = 0; j < T.dim; j++) {
+                const float x = qi[j], dl = x - lc[j], dr = x - rc[j];
+                l = fmaf(dl, dl, l);
+                r = fmaf(dr, dr, r);
+            }
         }
         if (!(fabsf(l - r) > 6.1035156e-5f * (l + r)) || T.dim > 1024) {
             l = 0.f, r = 0.f;
