@@ -723,6 +723,7 @@ void options_from_env(Options& o) {
     o.first_pass = std::max(-1, std::min(2, env_int("SCHT_FIRST_PASS", o.first_pass)));
     o.rescorer_sleep_ns = std::max(0, env_int("SCHT_RESCORER_SLEEP_NS", o.rescorer_sleep_ns));
     o.tc_recheck = env_int("SCHT_TC_RECHECK", o.tc_recheck) ? 1 : 0;
+    o.lazy_seed = env_int("SCHT_LAZY_SEED", o.lazy_seed) ? 1 : 0;
     o.ring_wait_ns = std::max(0, env_int("SCHT_RING_WAIT_NS", o.ring_wait_ns));
     {
         const int ring = env_int("SCHT_TC_RING", o.tc_ring);

@@ -46,15 +46,20 @@ int pick_variant(const scht_handle* h, int K) {
     return -1;
 }
 
-template <int NW, int MINB, bool FULL, int STAGES = kStages>
-int launch_scan_t(scht_handle* h, const ScanParams& P, cudaStream_t s) {
+template <int NW, int MINB, bool FULL, int STAGES, bool LAZY>
+int launch_scan_l(scht_handle* h, const ScanParams& P, cudaStream_t s) {
     size_t smem = scan_smem_bytes(NW, P.T.dpad, P.K, STAGES);
-    CU_TRY(cudaFuncSetAttribute(k_scan<NW, MINB, FULL, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_scan<NW, MINB, FULL, STAGES, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int tq = NW * kQPerWarp;
     int n_tiles = (P.nq + tq - 1) / tq;
-    k_scan<NW, MINB, FULL, STAGES><<<n_tiles, (NW + 1) * 32, smem, s>>>(P);
+    k_scan<NW, MINB, FULL, STAGES, LAZY><<<n_tiles, (NW + 1) * 32, smem, s>>>(P);
     CU_TRY(cudaGetLastError());
     return SCHT_OK;
+}
+template <int NW, int MINB, bool FULL, int STAGES = kStages>
+int launch_scan_t(scht_handle* h, const ScanParams& P, cudaStream_t s) {
+    if (P.lazy_seed && P.mode == kScanSeed) return launch_scan_l<NW, MINB, FULL, STAGES, true>(h, P, s);
+    return launch_scan_l<NW, MINB, FULL, STAGES, false>(h, P, s);
 }
 int launch_scan(scht_handle* h, int variant, const ScanParams& P, cudaStream_t s) {
     const bool full = (P.T.dpad % kRowsPerStage) == 0;
@@ -132,6 +137,7 @@ void fill_scan_params(scht_handle* h, ScanParams& P, const float* d_q, int nq, i
     P.K = K;
     P.pos_lo = h->T.pos_lo;
     P.pos_hi = h->T.pos_hi;
+    P.lazy_seed = h->bs.lazy_seed;
     P.range_groups = h->T.n_cuts;
     P.state = h->state.as<uint64_t>();
     P.ranges = h->ranges.as<int2>();
@@ -154,7 +160,8 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
 
 // Phase 1 of a batch.  kind: kBatchTree / kBatchPartial / kBatchBrute (the brute-force entry seeds through the tree too: the
 // seed lists only provide its bound).  The seed scan covers the handle's resident positions.
-int batch_seed(scht_handle* h, const float* d_q, int nq, int K, int kind, int leaf_lo, int leaf_hi, cudaStream_t s, scht_stats* st, bool timed) {
+int batch_seed(scht_handle* h, const float* d_q, int nq, int K, int kind, int leaf_lo, int leaf_hi, cudaStream_t s, scht_stats* st, bool timed,
+               bool lazy) {
     (void)leaf_lo;
     (void)leaf_hi;
     (void)st;
@@ -168,6 +175,7 @@ int batch_seed(scht_handle* h, const float* d_q, int nq, int K, int kind, int le
     h->bs.kind = kind;
     h->bs.nq = nq;
     h->bs.K = K;
+    h->bs.lazy_seed = lazy ? 1 : 0;
     const int n_tiles = (nq + h->bs.tq - 1) / h->bs.tq;
     const int n_tiles_tc = (nq + kTcQ - 1) / kTcQ;
     CU_TRY(h->q_leaf.reserve((size_t)nq * 4));
@@ -577,7 +585,13 @@ namespace {
 // one whole batch on the device (both phases; the brute-force entry turns its seed lists into the bound)
 int run_batch(scht_handle* h, const float* d_q, int nq, int K, int kind, int leaf_lo, int leaf_hi, const QueryOut& out, cudaStream_t s, scht_stats* st,
               bool timed) {
-    int rc = batch_seed(h, d_q, nq, K, kind, leaf_lo, leaf_hi, s, st, timed);
+    // Lazy seed scan (ScanParams::lazy_seed) when the main scan will not rely on "the seed pages are done": the brute-force entry
+    // (lists start empty, the seed only provides the bound) and tree batches whose main scan is the prefilter scan, which re-scans
+    // every listed page anyway -- guessed from the handle's last eligibility verdict; a wrong guess costs the exact scan a second
+    // look at the seed pages, never a result bit.
+    const bool lazy = h->opt.lazy_seed && h->I.kp > 0 && h->opt.tc_mode != 0 &&
+                      (kind == kBatchBrute ? h->opt.brute_tc != 0 : (kind == kBatchTree && (h->opt.tc_mode == 1 || h->elig_last > 0)));
+    int rc = batch_seed(h, d_q, nq, K, kind, leaf_lo, leaf_hi, s, st, timed, lazy);
     if (rc) return rc;
     const float* ext = nullptr;
     bool need_bound = kind == kBatchBrute;
@@ -812,6 +826,7 @@ const OptEntry kOptions[] = {
     {"first_pass", &Options::first_pass, -1, 2},
     {"tc_ring", &Options::tc_ring, 0, 1024},
     {"tc_recheck", &Options::tc_recheck, 0, 1},
+    {"lazy_seed", &Options::lazy_seed, 0, 1},
     {"ring_wait_ns", &Options::ring_wait_ns, 0, 1000000},
     {"groups", &Options::groups, -1, 1 << 20},
 };

@@ -87,6 +87,7 @@ struct Options {
     int tc_ring = 0;            // k_scan_tc: survivor ring entries per epilogue warp: 0 auto (64 for K <= 32, else 256) or a power of two in 32..1024
     int ring_wait_ns = 1000;    // k_scan_tc: pause of an epilogue warp between polls while its survivor ring is full (40 -> 1000 ns: K=100 main scan 33.6 -> 32.3 ms, its polls share an issue port with a rescorer)
     int tc_recheck = 1;         // k_scan_tc, wide points: ring entries carry the prefilter value, stale ones are dropped before the exact evaluation
+    int lazy_seed = 1;          // seed scan by fast-path distances, exact evaluation of the K entries that are left (batches whose main scan is the prefilter scan)
     int pipeline_split = 0;     // split a single-batch scht_query call into this many sub-batches so that its copies overlap (0/1: off)
 };
 
@@ -116,7 +117,7 @@ struct scht_handle {
     long long elig_sig = -1;
     int64_t tc_batches = 0;
     // state of the batch between batch_seed and batch_main
-    struct { int variant = 0, tq = 0, launches = 0, scans = 0, kind = 0, nq = 0, K = 0; } bs;
+    struct { int variant = 0, tq = 0, launches = 0, scans = 0, kind = 0, nq = 0, K = 0, lazy_seed = 0; } bs;
     std::vector<int> h_leaf_start, h_leaf_count, h_parent;
     std::vector<scht::NodeRec> h_rec;
     scht::DevBuf q[2], idx[2], d2[2], dist[2];  // per pipeline slot
@@ -150,7 +151,8 @@ struct QueryOut {
 };
 enum BatchKind : int { kBatchTree = 0, kBatchBrute = 1, kBatchPartial = 2 };
 // phase 1: descent, bucketing, seed scan (lists -> h->state); phase 2: (eligibility, page selection / traversal, main scan)
-int batch_seed(scht_handle* h, const float* d_q, int nq, int K, int kind, int leaf_lo, int leaf_hi, cudaStream_t s, scht_stats* st, bool timed);
+int batch_seed(scht_handle* h, const float* d_q, int nq, int K, int kind, int leaf_lo, int leaf_hi, cudaStream_t s, scht_stats* st, bool timed,
+               bool lazy = false);
 int batch_bounds(scht_handle* h, int nq, int K, float* d_bound_out, cudaStream_t s);  // bound[qid] = K-th seed distance^2 (FLT_MAX: list not full)
 int batch_main(scht_handle* h, const float* d_q, int nq, int K, int kind, int leaf_lo, int leaf_hi, const float* d_ext_bound, const QueryOut& out,
                cudaStream_t s, scht_stats* st, bool timed);

@@ -246,6 +246,9 @@ struct ScanParams {
     int mode;
     int write_mode;        // kWriteFinal / kWriteState / kWriteKeys
     int pos_lo, pos_hi;    // only positions in [pos_lo,pos_hi) may enter the lists (sharded-dataset mode)
+    int lazy_seed;         // the batch's seed scan (kScanSeed) keeps its lists by FAST-path distances and evaluates only the K entries
+                           //   that are left with the reference arithmetic at the end (the lists it writes are exact keys of real points,
+                           //   but not necessarily the K nearest of the seed pages: a later kScanList pass must not skip those pages)
     const int2* ranges;    // [n_tiles][kMaxCuts][kJobRanges] page ranges [x,y) (kScanList)
     const int* n_ranges;   // [n_tiles][kMaxCuts]
     int range_groups;      // groups of kJobRanges ranges to walk per tile (traversal: T.n_cuts, page selection: kMaxCuts)
@@ -402,7 +405,8 @@ struct PageWalk {
 
 // FULL: dpad is a multiple of 16, every stage holds 16 rows and the row loop is straight-line code.
 // STAGES: depth of the slice ring (4; 2 for wide points, whose query block would otherwise cost the third resident CTA).
-template <int NW, int MINB, bool FULL, int STAGES = kStages>
+// LAZY: the seed scan of a batch with ScanParams::lazy_seed (a template parameter so that the other passes keep their code)
+template <int NW, int MINB, bool FULL, int STAGES = kStages, bool LAZY = false>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P) {
     constexpr int TQ = NW * kQPerWarp;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -491,7 +495,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
         cnt = P.n_ranges + (size_t)tile * kMaxCuts;
         n_groups = P.range_groups;
         stride = kJobRanges;
-        n_skip = n_seed;  // pages of the seed scan are already in the lists
+        n_skip = P.lazy_seed ? 0 : n_seed;  // pages of the seed scan are already in the lists (unless the seed scan was lazy)
     }
     PageWalk walk(list, cnt, n_groups, stride, seed_rg, n_skip);
     const int n_slices = (dpad + kRowsPerStage - 1) / kRowsPerStage;
@@ -529,6 +533,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
         thr[qi] = (qw0 + qi < nq_tile) ? fminf(fminf(kth * 1.000001f, 3.402823466e+38f), exts[qw0 + qi]) : -1.f;
     }
     const bool brute = (P.mode == kScanAll);
+    constexpr bool lazy = LAZY;  // (launched for kScanSeed with P.lazy_seed only)
     // Narrow points (the whole page is ONE stage): the stage is handed back to the producer only after the page's exact
     // path, which then reads its candidates' coordinates from shared memory instead of L2 (a ~700-cycle round trip per
     // batch of 8 loads, most of the seed scan's time).
@@ -689,6 +694,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
                     // loads first (8 dims in flight), then the sequential reference chain: the chain would otherwise
                     // serialise one round trip per dimension.  A held stage is read from shared memory (dim-major);
                     // otherwise the point's row comes from the row-major copy (two 16-byte loads per 8 dims)
+                    // lazy seed scan: a plain FP32 evaluation (two FMA chains) stands in for the reference chain; what is left in
+                    // the lists at the end is evaluated exactly (below)
+                    float f0 = 0.f, f1 = 0.f;
                     if (hold_stage) {
                         const float* pg = stage_mem + (size_t)held_st * kRowsPerStage * kPage + in_page;
                         for (int j0 = 0; j0 < T.dim; j0 += 8) {
@@ -697,7 +705,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
                             for (int u = 0; u < 8; u++) pv[u] = (j0 + u < T.dim) ? pg[(size_t)(j0 + u) * kPage] : 0.f;
 #pragma unroll
                             for (int u = 0; u < 8; u++)
-                                if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
+                                if (j0 + u < T.dim) {
+                                    const float d = pv[u] - qq[(j0 + u) * TQ];
+                                    if (!lazy) d2 = ref_acc_sq(d2, d);
+                                    else if (u & 1) f1 = fmaf(d, d, f1);
+                                    else f0 = fmaf(d, d, f0);
+                                }
                         }
                     } else {
                         const float4* pr = reinterpret_cast<const float4*>(T.rows + (size_t)pos * dpad);
@@ -708,9 +721,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
                             const float pv[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
 #pragma unroll
                             for (int u = 0; u < 8; u++)
-                                if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
+                                if (j0 + u < T.dim) {
+                                    const float d = pv[u] - qq[(j0 + u) * TQ];
+                                    if (!lazy) d2 = ref_acc_sq(d2, d);
+                                    else if (u & 1) f1 = fmaf(d, d, f1);
+                                    else f0 = fmaf(d, d, f0);
+                                }
                         }
                     }
+                    if (lazy) d2 = f0 + f1;
                     n_exact++;
                     cand = (d2 < 3.402823466e+38f) && (pos >= P.pos_lo) && (pos < P.pos_hi);
                 }
@@ -751,6 +770,80 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_scan(const ScanParams P
         if (hold_stage) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[held_st]);
+        }
+    }
+
+    // ---- lazy seed scan: the entries that are left get their reference distances (the warp's 8 lists together, 32 entries
+    // per round), then every list is put back in order (the fast and the exact order differ on near-ties only)
+    if (lazy) {
+        __syncwarp();
+        const int total = kQPerWarp * K;
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < total) {
+                const int qi = e / K;
+                uint64_t* slot = my_lists + e;  // (= my_lists + qi * K + k)
+                const uint64_t key = *slot;
+                if (qw0 + qi < nq_tile && key != kEmptyKey) {
+                    const int pos = (int)((uint32_t)key & 0x7fffffffu);
+                    const float* qq = qs + qw0 + qi;
+                    float d2 = 0.f;
+                    if (T.rows) {
+                        const float4* pr = reinterpret_cast<const float4*>(T.rows + (size_t)pos * dpad);
+                        prefetch_row(pr, dpad);
+                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                            const float4 x = __ldg(pr + (j0 >> 2));
+                            const float4 y = (j0 + 4 < dpad) ? __ldg(pr + (j0 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float pv[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
+                        }
+                    } else {
+                        const float* pg = T.pages + (size_t)(pos / kPage) * dpad * kPage + (pos % kPage);
+                        for (int j0 = 0; j0 < T.dim; j0 += 8) {
+                            float pv[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) pv[u] = (j0 + u < T.dim) ? __ldg(pg + (size_t)(j0 + u) * kPage) : 0.f;
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (j0 + u < T.dim) d2 = ref_acc_sq(d2, pv[u] - qq[(j0 + u) * TQ]);
+                        }
+                    }
+                    *slot = (d2 < 3.402823466e+38f) ? (((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)key) : kEmptyKey;
+                    n_exact++;
+                }
+            }
+        }
+        __syncwarp();
+        for (int qi = 0; qi < kQPerWarp; qi++) {
+            if (qw0 + qi >= nq_tile) break;
+            uint64_t* L = my_lists + (size_t)qi * K;
+            bool bad = false;
+            for (int k = lane; k + 1 < K; k += 32) bad |= L[k] > L[k + 1];
+            if (!__any_sync(0xffffffffu, bad)) continue;
+            // stable rank sort (keys of real points are unique; empty slots compare equal and keep their order)
+            uint64_t mine[4];
+            int rank[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const int k = s * 32 + lane;
+                mine[s] = (k < K) ? L[k] : kEmptyKey;
+                rank[s] = k;
+                if (k < K) {
+                    int r = 0;
+                    for (int j = 0; j < K; j++) {
+                        const uint64_t o = L[j];
+                        r += (o < mine[s] || (o == mine[s] && j < k)) ? 1 : 0;
+                    }
+                    rank[s] = r;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+                if (s * 32 + lane < K) L[rank[s]] = mine[s];
+            __syncwarp();
         }
     }
 

@@ -207,6 +207,36 @@ def test_survivor_ring_depth(pkg, orc):
     ix.close()
 
 
+@pytest.mark.parametrize("dim,K", [(24, 10), (12, 10), (24, 100), (130, 5)])
+def test_lazy_seed_scan(pkg, orc, dim, K):
+    """option lazy_seed: the seed scan keeps its lists by fast-path distances and evaluates only what is left with the
+    reference arithmetic; same bits as the exact seed scan, for the tree query (prefilter and exact main scan) and the
+    brute-force entry; duplicates of the data set among the queries give exact ties"""
+    rng = np.random.default_rng(31 + dim)
+    n, nq = 50000, 2500
+    c = rng.random((30, dim))
+    data = (c[rng.integers(0, 30, n)] + 0.03 * rng.standard_normal((n, dim))).astype(np.float32)
+    data[1000:1200] = data[2000:2200]  # duplicate points: equal distances, ties by position / original index
+    q = (c[rng.integers(0, 30, nq)] + 0.03 * rng.standard_normal((nq, dim))).astype(np.float32)
+    q[:100] = data[2000:2100]
+    ht = pkg.HostTree(data, 0.004, seed=1)
+    oi, od2, _, _, _ = orc.knn(ht, q, K, alg=2)
+    obi, obd2, _ = orc.brute_force(data, q[:300], K)
+    ix = pkg.Index(ht)
+    for tc in (1, 0):  # prefilter forced (the seed scan is lazy from the first batch on) / exact main scan (never lazy for tree batches)
+        ix.set_option("tc", tc)
+        for lazy in (1, 0):
+            ix.set_option("lazy_seed", lazy)
+            for rep in range(2):
+                idx, d2 = ix.query(q, K)
+                assert_bit_equal(idx, oi, "idx tc=%d lazy=%d" % (tc, lazy))
+                assert_bit_equal(d2, od2, "dist2 tc=%d lazy=%d" % (tc, lazy))
+            bi, bd2 = ix.brute_force(q[:300], K)
+            assert_bit_equal(bi, obi, "brute idx tc=%d lazy=%d" % (tc, lazy))
+            assert_bit_equal(bd2, obd2, "brute dist2 tc=%d lazy=%d" % (tc, lazy))
+    ix.close()
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 def test_pipelined_batches(pkg, orc, pinned):
     """a scht_query call of many batches overlaps its copies with the kernels (two copy streams, pinned staging for
