@@ -173,7 +173,7 @@ int scht_create_shard(const scht_tree_desc* tree, int device, int32_t leaf_begin
  * the defaults read when the handle is created.  Names: "tc" (0 off / 1 always / 2 auto), "tc_split", "tc_issuers",
  * "tc_n256", "scan_variant", "scan_stages", "traverse_sampling", "sample_reuse", "seed_points", "page_select",
  * "brute_tc", "pipeline", "pipeline_split", "first_pass", "rescorer_sleep_ns", "tc_ring" (0 or a power of two in
- * 32..1024), "tc_recheck", "ring_wait_ns"; "groups" can only be read (fixed at creation).  Unknown name or value out
+ * 32..1024), "tc_recheck", "ring_wait_ns", "lazy_seed"; "groups" can only be read (fixed at creation).  Unknown name or value out
  * of range -> SCHT_ERR_INVALID_ARG. */
 int scht_set_option(scht_handle* h, const char* name, int64_t value);
 int scht_get_option(const scht_handle* h, const char* name, int64_t* value);
