@@ -21,7 +21,11 @@
 // Two issue streams and two double-buffered epilogue groups hide the hand-off latencies (mbarrier waits, MMA issue,
 // commits: ~900 cycles per page for a single issuer).  The last four warps are the RESCORERS: rescorer r consumes the rings of
 // the four epilogue warps of lane quadrant r, re-evaluates the survivors exactly, owns the quadrant's 32 top-K lists
-// (no locks) and publishes the tightened bounds, so the MMA->epilogue pipeline never waits for an exact evaluation.
+// (no locks) and publishes the tightened bounds, so the MMA->epilogue pipeline waits for an exact evaluation only when a ring is
+// full.  The rings are deliberately SHALLOW for short lists (64 entries per epilogue warp for K <= 32): a survivor that waits goes
+// stale while its query's bound tightens, and the back-pressure of a full ring is what keeps the number of exact evaluations down
+// (DESIGN.md 4b).  For wide points the entries also carry the pair's accumulator value, and the rescorer repeats the epilogue's
+// test against the bound of the moment before it spends a row fetch and an FP64 chain on an entry (TcScanParams::recheck).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -55,7 +59,7 @@ struct TcScanParams {
                              //    issuer that skips the other parity's pages would run a whole ring round ahead of the producer, and a
                              //    parity wait cannot tell round r from round r+2)
     int n_stages;            // slice stages in shared memory (3..kTcMaxStages)
-    int queue_cap;           // ring entries per epilogue warp (power of two, kTcQueueCap..kTcQueueCapMax)
+    int queue_cap;           // ring entries per epilogue warp (power of two, 32..kTcQueueCapMax; the launcher picks 64 for K <= 32, else kTcQueueCap)
     int recheck;             // wide points: ring entries carry the pair's prefilter value and the rescorer drops an entry that the query's
                              //   bound has overtaken while it waited (needs n_slots <= 2^27)
     int n_seg;               // page segments per tile (>= 1): CTA b scans segment b / n_tiles of tile b % n_tiles and, when
